@@ -1,0 +1,215 @@
+/*
+ * kyd.h -- C ABI of libkyd.so, the B200 (sm_100a) rendering core for ky's per-pixel Monte Carlo
+ * integrator loop.
+ *
+ * Drop-in boundary: everything below replaces the BODY of
+ *     void integrator_t::render(scene_t*, sampler_t*, film_t*)        reference ky.cpp:3689-3729
+ * (pixel loop + spp loop + virtual Li() + scene_t::intersect + BSDF / light sampling), and nothing
+ * else.  The host side keeps ky's class surface (include/ky.hpp); its integrator_t::render()
+ * flattens scene / camera / integrator parameters into the PODs declared here, calls
+ * kyd_render(), and feeds the returned pixels to film_t::add_color() (ky.cpp:1586, 3726).
+ *
+ * Conventions
+ *   - plain C, plain pointers and sizes; the caller owns every pointer it passes in; the
+ *     library copies what it needs during the call.
+ *   - every function returns 0 on success, a KYD_ERR_* code otherwise; kyd_last_error()
+ *     returns the message (the reference throws from LOG_ERROR, ky.cpp:75-82; the C++ host
+ *     wrapper rethrows non-zero codes as std::runtime_error).
+ *   - there is no CPU fallback: without a CUDA device every entry point fails with
+ *     KYD_ERR_CUDA.
+ *   - one host thread per context at a time (the reference's render() is not re-entrant
+ *     either: it owns the film rows it writes, ky.cpp:3696-3728).
+ */
+#ifndef KYD_H
+#define KYD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KYD_VERSION 1
+
+enum kyd_error
+{
+    KYD_OK = 0,
+    KYD_ERR_INVALID = 1,   /* bad argument / unsupported enum value */
+    KYD_ERR_CUDA = 2,      /* CUDA runtime error, or no device */
+    KYD_ERR_NO_SCENE = 3,  /* kyd_render before kyd_upload_scene */
+    KYD_ERR_LIMIT = 4      /* scene larger than KYD_MAX_* */
+};
+
+enum { KYD_MAX_SURFACES = 64, KYD_MAX_SHAPES = 64, KYD_MAX_MATERIALS = 32, KYD_MAX_LIGHTS = 16 };
+
+/* ---- flattened scene: one POD per reference object ------------------------------------------- */
+
+/* shape_t subclasses, ky.cpp:1100-1519 */
+enum kyd_shape_kind { KYD_SHAPE_SPHERE = 0, KYD_SHAPE_RECTANGLE = 1, KYD_SHAPE_TRIANGLE = 2, KYD_SHAPE_DISK = 3 };
+
+typedef struct kyd_shape
+{
+    int32_t kind;
+    float p0[3];      /* sphere: center_; disk: position_; triangle/rectangle: p0_ */
+    float p1[3];      /* triangle/rectangle: p1_ */
+    float p2[3];      /* triangle/rectangle: p2_ */
+    float p3[3];      /* rectangle: p3_ */
+    float normal[3];  /* rectangle/triangle/disk: stored normal_ (after flip_normal), ky.cpp:1105,1174,1256 */
+    float radius;     /* sphere/disk radius_ */
+    float radius_sq;  /* sphere radius_sq_ as the constructor rounds it, ky.cpp:1332 */
+    float area;       /* shape_t::area(), ky.cpp:1141,1222,1304,1401 */
+} kyd_shape;
+
+/* material_t subclasses, ky.cpp:2579-2682 */
+enum kyd_material_kind { KYD_MAT_MATTE = 0, KYD_MAT_MIRROR = 1, KYD_MAT_GLASS = 2, KYD_MAT_PLASTIC = 3 };
+
+typedef struct kyd_material
+{
+    int32_t kind;
+    float diffuse[3];       /* matte diffuse_color_; plastic diffuse_color_ */
+    float specular[3];      /* mirror specular_color_; plastic specular_color_; glass reflection_color_ */
+    float transmission[3];  /* glass transmission_color_ */
+    float eta;              /* glass eta_ (eta_i is 1, ky.cpp:2630) */
+    float exponent;         /* plastic exponent_ */
+    float diffuse_probability;   /* plastic diffuse_probility_, ky.cpp:2657 */
+    float specular_probability;  /* plastic specular_probility_, ky.cpp:2658 */
+} kyd_material;
+
+/* light_t subclasses, ky.cpp:2810-3062 */
+enum kyd_light_kind { KYD_LIGHT_POINT = 0, KYD_LIGHT_DIRECTION = 1, KYD_LIGHT_AREA = 2, KYD_LIGHT_ENVIRONMENT = 3 };
+
+typedef struct kyd_light
+{
+    int32_t kind;
+    float color[3];      /* point intensity_; direction irradiance_; area/environment radiance_ */
+    float position[3];   /* point light world_position_ */
+    float direction[3];  /* direction light world_direction_ (normalised by its ctor, ky.cpp:2874) */
+    float world_radius;  /* direction/environment world_radius_ from preprocess(), ky.cpp:3555-3574 */
+    int32_t shape;       /* area light shape_ as an index into shapes[] (NOT derived from surfaces) */
+} kyd_light;
+
+/* surface_t, ky.cpp:3071-3089: three independent links */
+typedef struct kyd_surface
+{
+    int32_t shape;
+    int32_t material;
+    int32_t area_light;  /* index into lights[] or -1 */
+} kyd_surface;
+
+/* camera_t after its constructor ran, ky.cpp:1864-1880 */
+typedef struct kyd_camera
+{
+    float position[3];
+    float front[3];       /* normalised */
+    float right[3];       /* scaled by tan(fov/2) * aspect */
+    float up[3];          /* scaled by tan(fov/2) */
+    float resolution[2];  /* film_t::get_resolution(): the SUB-film size for film_grid_t, ky.cpp:1815 */
+    float origin_push;    /* 0 for ky; 140 for the smallpt camera (smallpt_rewrite.cpp:676) */
+} kyd_camera;
+
+typedef struct kyd_scene_desc
+{
+    kyd_camera camera;
+    int32_t shape_count;     const kyd_shape* shapes;
+    int32_t material_count;  const kyd_material* materials;
+    int32_t light_count;     const kyd_light* lights;       /* scene_t::light_list() order */
+    int32_t surface_count;   const kyd_surface* surfaces;   /* scene_t surface_list_ order = traversal order */
+    int32_t environment_light;                              /* scene_t::environment_light_ as light index or -1 */
+} kyd_scene_desc;
+
+/* ---- render request --------------------------------------------------------------------------- */
+
+/* integrator_enum_t, ky.cpp:3625-3654 (same numeric values) */
+enum kyd_integrator
+{
+    KYD_INT_POSITION = 0, KYD_INT_NORMAL = 1, KYD_INT_BASECOLOR = 2,   /* debug_integrator_t, ky.cpp:4094 */
+    KYD_INT_DIRECT_LIGHTING = 6,                                        /* direct_lighting_t, ky.cpp:4125 */
+    KYD_INT_SIMPLE_PT_RECURSION = 8,                                    /* ky.cpp:4191 */
+    KYD_INT_PT_RECURSION = 9,                                           /* ky.cpp:4305 */
+    KYD_INT_PT_RECURSION_DEFERED = 10,                                  /* ky.cpp:4409 */
+    KYD_INT_PT_ITERATION = 11                                           /* ky.cpp:4523 */
+};
+
+/* direct_sample_enum_t, ky.cpp:3608-3623 (same numeric values) */
+enum kyd_direct_sample
+{
+    KYD_DS_IDLE = 0, KYD_DS_BSDF = 4, KYD_DS_LIGHT = 8, KYD_DS_BSDF_MIS = 16, KYD_DS_LIGHT_MIS = 32, KYD_DS_BOTH_MIS = 48
+};
+
+/* lighting_enum_t, ky.cpp:3591-3603 (lighting filter of render_lighting_enum, ky.cpp:4907-4935) */
+enum kyd_lighting
+{
+    KYD_LIGHTING_EMIT = 1, KYD_LIGHTING_DIRECT = 2, KYD_LIGHTING_INDIRECT = 4, KYD_LIGHTING_ALL = 31
+};
+
+enum kyd_sampler
+{
+    KYD_SAMPLER_LCG48 = 0,  /* counter-seeded 48-bit LCG, the contract of DESIGN.md "Sampling" */
+    KYD_SAMPLER_DEBUG = 1   /* debug_sampler_t: every draw is 0.5, ky.cpp:922-947 */
+};
+
+enum kyd_render_flags
+{
+    KYD_FLAG_CLAMP = 1u,       /* film = clamp01(sum), what render() hands to add_color (ky.cpp:3726);
+                                  without it the raw partial sum is returned (multi-GPU partials) */
+    KYD_FLAG_FUSED = 2u,       /* one fused kernel per bounce instead of the split wavefront stages */
+    KYD_FLAG_ACCUMULATE = 4u   /* device film: add to what the buffer holds instead of overwriting */
+};
+
+typedef struct kyd_render_desc
+{
+    int32_t width, height;       /* film (or sub-film) resolution in pixels */
+    int32_t spp;                 /* samples per pixel of the WHOLE job: every sample weighs 1/spp (ky.cpp:3717) */
+    int32_t sample_begin;        /* this call renders sample indices [sample_begin, sample_end) of each pixel; */
+    int32_t sample_end;          /* (0, spp) is the whole job; sub-ranges are what a multi-GPU split hands out */
+    int32_t integrator;          /* enum kyd_integrator */
+    int32_t max_depth;           /* path_integrator_t::max_path_depth_, ky.cpp:4182 */
+    int32_t direct_sample;       /* enum kyd_direct_sample */
+    int32_t lighting;            /* enum kyd_lighting; KYD_LIGHTING_ALL unless rendering render_lighting_enum panels */
+    int32_t sampler;             /* enum kyd_sampler */
+    uint64_t seed;               /* rng_t's seed, 1234 in the reference (ky.cpp:833) */
+    uint32_t flags;              /* enum kyd_render_flags */
+    uint32_t reserved;
+} kyd_render_desc;
+
+typedef struct kyd_stats
+{
+    uint64_t samples;           /* camera paths started by the last kyd_render call */
+    uint64_t rays;              /* scene_t::intersect-equivalent queries: primary + bsdf + shadow rays */
+    uint64_t kernel_launches;   /* kernels launched by the last call */
+    double device_ms;           /* CUDA-event time of the last call's kernels (excludes host copies) */
+    double stage_ms[8];         /* raygen, intersect, shade, light_sample, shadow, scatter, accumulate, fused */
+} kyd_stats;
+
+typedef struct kyd_ctx kyd_ctx;
+
+/* creates a context on CUDA device `device` (cudaSetDevice ordinal) with its own stream */
+int kyd_create(kyd_ctx** out_ctx, int device);
+void kyd_destroy(kyd_ctx* ctx);
+const char* kyd_last_error(const kyd_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/* copies the flattened scene to the device (replaces the previous one) */
+int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* scene);
+
+/* renders into HOST memory: film_rgb[height*width*3], row-major, y down (film_t::pixels_, ky.cpp:1574).
+   The device->host copy is part of the call. */
+int kyd_render(kyd_ctx* ctx, const kyd_render_desc* desc, float* film_rgb);
+
+/* same, but film_rgb is a DEVICE pointer on the context's device (what a multi-GPU driver reduces
+   with NCCL before the final clamp).  Runs asynchronously on `cuda_stream` (a cudaStream_t, or NULL
+   for the context's own stream, in which case the call synchronises before returning). */
+int kyd_render_device(kyd_ctx* ctx, const kyd_render_desc* desc, float* film_rgb_device, void* cuda_stream);
+
+/* film[i] = clamp01(film[i]) on the device, n floats: the final step of a multi-GPU job after the reduce */
+int kyd_clamp_device(kyd_ctx* ctx, float* film_rgb_device, int64_t n, void* cuda_stream);
+
+int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out);
+
+/* size in paths of one wavefront (0 = choose from the film size); tuning knob, results do not depend on it */
+int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* KYD_H */
