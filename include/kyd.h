@@ -175,7 +175,8 @@ typedef struct kyd_render_desc
 typedef struct kyd_stats
 {
     uint64_t samples;           /* camera paths started by the last kyd_render call */
-    uint64_t rays;              /* scene_t::intersect-equivalent queries: primary + bsdf + shadow rays */
+    uint64_t rays;              /* scene queries the reference issues for these samples (scene_t::intersect + occluded calls) */
+    uint64_t rays_traced;       /* scene queries the device actually traversed (it skips those that cannot change the result) */
     uint64_t kernel_launches;   /* kernels launched by the last call */
     double device_ms;           /* CUDA-event time of the last call's kernels (excludes host copies) */
     double stage_ms[8];         /* raygen, intersect, shade, light_sample, shadow, scatter, accumulate, fused */

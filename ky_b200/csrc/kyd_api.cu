@@ -1,0 +1,379 @@
+// kyd_api.cu -- the C ABI of include/kyd.h: context, scene upload, render orchestration.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kyd_internal.h"
+
+using namespace kyd;
+
+struct kyd_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    std::string error;
+
+    bool has_scene = false;
+    DevScene scene{};
+    unsigned long long scene_generation = 0;
+
+    float* film_dev = nullptr;      // staging film for kyd_render (host destination)
+    size_t film_capacity = 0;       // floats
+    float* film_pinned = nullptr;   // pinned bounce buffer for the device->host copy
+    size_t pinned_capacity = 0;
+
+    DevCounters* counters_dev = nullptr;
+    DevCounters* counters_pinned = nullptr;
+    kyd_stats stats{};
+
+    WaveBuffers wave;
+    int64_t wave_paths = 0;
+};
+
+namespace {
+
+std::string g_create_error;
+
+// c_scene is one symbol per device: remember which context's scene it holds
+std::mutex g_scene_mutex;
+const kyd_ctx* g_scene_owner[64] = {};
+unsigned long long g_scene_owner_generation[64] = {};
+
+int fail(kyd_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->error = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+#define KYD_CUDA(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, KYD_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+float3 f3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+
+DevShape convert_shape(const kyd_shape& s)
+{
+    DevShape d{};
+    d.kind = s.kind;
+    d.p0 = f3(s.p0); d.p1 = f3(s.p1); d.p2 = f3(s.p2); d.p3 = f3(s.p3); d.n = f3(s.normal);
+    d.radius = s.radius; d.radius_sq = s.radius_sq; d.area = s.area;
+    return d;
+}
+
+int ensure_film(kyd_ctx* ctx, size_t floats)
+{
+    if (floats <= ctx->film_capacity)
+        return KYD_OK;
+    if (ctx->film_dev) cudaFree(ctx->film_dev);
+    ctx->film_dev = nullptr;
+    ctx->film_capacity = 0;
+    KYD_CUDA(ctx, cudaMalloc(&ctx->film_dev, floats * sizeof(float)));
+    ctx->film_capacity = floats;
+    return KYD_OK;
+}
+
+int ensure_pinned(kyd_ctx* ctx, size_t floats)
+{
+    if (floats <= ctx->pinned_capacity)
+        return KYD_OK;
+    if (ctx->film_pinned) cudaFreeHost(ctx->film_pinned);
+    ctx->film_pinned = nullptr;
+    ctx->pinned_capacity = 0;
+    KYD_CUDA(ctx, cudaMallocHost(&ctx->film_pinned, floats * sizeof(float)));
+    ctx->pinned_capacity = floats;
+    return KYD_OK;
+}
+
+int validate(kyd_ctx* ctx, const kyd_render_desc* d)
+{
+    if (!d) return fail(ctx, KYD_ERR_INVALID, "render desc is null");
+    if (d->width <= 0 || d->height <= 0) return fail(ctx, KYD_ERR_INVALID, "film size must be positive");
+    if (d->width >= 65536 || d->height >= 65536) return fail(ctx, KYD_ERR_INVALID, "film size must be below 65536 (sampler key)");
+    if (d->spp <= 0) return fail(ctx, KYD_ERR_INVALID, "spp must be positive");
+    if (d->sample_begin < 0 || d->sample_end < d->sample_begin || d->sample_end > (1 << 24))
+        return fail(ctx, KYD_ERR_INVALID, "bad sample range");
+    switch (d->integrator)
+    {
+    case KYD_INT_POSITION: case KYD_INT_NORMAL: case KYD_INT_BASECOLOR: case KYD_INT_DIRECT_LIGHTING:
+    case KYD_INT_PT_ITERATION:
+        break;
+    case KYD_INT_SIMPLE_PT_RECURSION: case KYD_INT_PT_RECURSION: case KYD_INT_PT_RECURSION_DEFERED:
+        if (d->max_depth > KYD_MAX_RECURSION - 1)
+            return fail(ctx, KYD_ERR_INVALID, "max_depth too large for a recursive integrator");
+        break;
+    default:
+        return fail(ctx, KYD_ERR_INVALID, "unsupported integrator_enum_t value");
+    }
+    switch (d->direct_sample)
+    {
+    case KYD_DS_IDLE: case KYD_DS_BSDF: case KYD_DS_LIGHT: case KYD_DS_BSDF_MIS: case KYD_DS_LIGHT_MIS: case KYD_DS_BOTH_MIS:
+        break;
+    default:
+        return fail(ctx, KYD_ERR_INVALID, "unsupported direct_sample_enum_t value");
+    }
+    if (d->sampler != KYD_SAMPLER_LCG48 && d->sampler != KYD_SAMPLER_DEBUG)
+        return fail(ctx, KYD_ERR_INVALID, "unsupported sampler");
+    if (d->max_depth < 0) return fail(ctx, KYD_ERR_INVALID, "max_depth must be >= 0");
+    return KYD_OK;
+}
+
+// makes the device's constant scene the one of this context
+int bind_scene(kyd_ctx* ctx, cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_scene_mutex);
+    int dev = ctx->device & 63;
+    if (g_scene_owner[dev] != ctx || g_scene_owner_generation[dev] != ctx->scene_generation)
+    {
+        KYD_CUDA(ctx, cudaDeviceSynchronize()); // another context's kernels may still read c_scene
+        upload_scene_constant(ctx->scene, stream);
+        KYD_CUDA(ctx, cudaGetLastError());
+        g_scene_owner[dev] = ctx;
+        g_scene_owner_generation[dev] = ctx->scene_generation;
+    }
+    return KYD_OK;
+}
+
+int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cudaStream_t stream, bool timed)
+{
+    RenderParams rp{};
+    rp.width = d->width; rp.height = d->height; rp.spp = d->spp;
+    rp.sample_begin = d->sample_begin; rp.sample_end = d->sample_end;
+    rp.integrator = d->integrator; rp.max_depth = d->max_depth; rp.direct_sample = d->direct_sample;
+    rp.lighting = d->lighting; rp.sampler = d->sampler; rp.seed = d->seed; rp.flags = d->flags;
+    rp.weight = (float)(1. / d->spp);
+
+    int rc = bind_scene(ctx, stream);
+    if (rc != KYD_OK) return rc;
+
+    KYD_CUDA(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(DevCounters), stream));
+    if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_begin, stream));
+
+    uint64_t launches = 0;
+    launch_render_pixels(rp, film_dev, ctx->counters_dev, stream);
+    launches += 1;
+    KYD_CUDA(ctx, cudaGetLastError());
+
+    if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_end, stream));
+    KYD_CUDA(ctx, cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_dev, sizeof(DevCounters), cudaMemcpyDeviceToHost, stream));
+
+    ctx->stats = kyd_stats{};
+    ctx->stats.samples = (uint64_t)d->width * d->height * (uint64_t)(d->sample_end - d->sample_begin);
+    ctx->stats.kernel_launches = launches;
+    return KYD_OK;
+}
+
+void finish_stats(kyd_ctx* ctx, bool timed)
+{
+    ctx->stats.rays = ctx->counters_pinned->rays;
+    ctx->stats.rays_traced = ctx->counters_pinned->rays_traced;
+    ctx->stats.stage_ms[7] = 0;
+    if (timed)
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
+        ctx->stats.device_ms = ms;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+int kyd_create(kyd_ctx** out_ctx, int device)
+{
+    if (!out_ctx) return fail(nullptr, KYD_ERR_INVALID, "out_ctx is null");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, KYD_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (kyd has no CPU fallback)");
+    if (device < 0 || device >= count)
+        return fail(nullptr, KYD_ERR_INVALID, "device ordinal out of range");
+
+    kyd_ctx* ctx = new kyd_ctx;
+    ctx->device = device;
+    auto cleanup = [&](const std::string& msg) { g_create_error = msg; kyd_destroy(ctx); return KYD_ERR_CUDA; };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    if ((e = cudaEventCreate(&ctx->ev_begin)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    if ((e = cudaMalloc(&ctx->counters_dev, sizeof(DevCounters))) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    if ((e = cudaMallocHost(&ctx->counters_pinned, sizeof(DevCounters))) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    memset(ctx->counters_pinned, 0, sizeof(DevCounters));
+    *out_ctx = ctx;
+    return KYD_OK;
+}
+
+void kyd_destroy(kyd_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    {
+        std::lock_guard<std::mutex> lock(g_scene_mutex);
+        if (g_scene_owner[ctx->device & 63] == ctx) g_scene_owner[ctx->device & 63] = nullptr;
+    }
+    free_wave_buffers(ctx->wave);
+    if (ctx->film_dev) cudaFree(ctx->film_dev);
+    if (ctx->film_pinned) cudaFreeHost(ctx->film_pinned);
+    if (ctx->counters_dev) cudaFree(ctx->counters_dev);
+    if (ctx->counters_pinned) cudaFreeHost(ctx->counters_pinned);
+    if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
+    if (ctx->ev_end) cudaEventDestroy(ctx->ev_end);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* kyd_last_error(const kyd_ctx* ctx)
+{
+    return ctx ? ctx->error.c_str() : g_create_error.c_str();
+}
+
+int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (!sc) return fail(ctx, KYD_ERR_INVALID, "scene desc is null");
+    if (sc->surface_count < 0 || sc->surface_count > KYD_MAX_SURFACES || sc->shape_count < 0 || sc->shape_count > KYD_MAX_SHAPES ||
+        sc->material_count < 0 || sc->material_count > KYD_MAX_MATERIALS || sc->light_count < 0 || sc->light_count > KYD_MAX_LIGHTS)
+        return fail(ctx, KYD_ERR_LIMIT, "scene exceeds KYD_MAX_* limits");
+
+    DevScene& d = ctx->scene;
+    memset(&d, 0, sizeof(d));
+    d.camera.position = f3(sc->camera.position);
+    d.camera.front = f3(sc->camera.front);
+    d.camera.right = f3(sc->camera.right);
+    d.camera.up = f3(sc->camera.up);
+    d.camera.res_x = sc->camera.resolution[0];
+    d.camera.res_y = sc->camera.resolution[1];
+    d.camera.push = sc->camera.origin_push;
+    d.n_surfaces = sc->surface_count;
+    d.n_lights = sc->light_count;
+    d.env_light = sc->environment_light;
+    if (d.env_light >= sc->light_count) return fail(ctx, KYD_ERR_INVALID, "environment_light index out of range");
+
+    for (int i = 0; i < sc->surface_count; ++i)
+    {
+        const kyd_surface& s = sc->surfaces[i];
+        if (s.shape < 0 || s.shape >= sc->shape_count || s.material < 0 || s.material >= sc->material_count ||
+            s.area_light < -1 || s.area_light >= sc->light_count)
+            return fail(ctx, KYD_ERR_INVALID, "surface index out of range");
+        if (sc->shapes[s.shape].kind < 0 || sc->shapes[s.shape].kind > KYD_SHAPE_DISK)
+            return fail(ctx, KYD_ERR_INVALID, "unknown shape kind");
+        d.surf_shape[i] = convert_shape(sc->shapes[s.shape]);
+        d.surf_material[i] = s.material;
+        d.surf_light[i] = s.area_light;
+    }
+    for (int i = 0; i < sc->material_count; ++i)
+    {
+        const kyd_material& m = sc->materials[i];
+        if (m.kind < 0 || m.kind > KYD_MAT_PLASTIC) return fail(ctx, KYD_ERR_INVALID, "unknown material kind");
+        DevMaterial& o = d.materials[i];
+        o.kind = m.kind;
+        o.diffuse = f3(m.diffuse); o.specular = f3(m.specular); o.transmission = f3(m.transmission);
+        o.eta = m.eta; o.exponent = m.exponent;
+        o.p_diffuse = m.diffuse_probability; o.p_specular = m.specular_probability;
+        // color_t / float_t is three divisions (ky.cpp:231); IEEE on the host == IEEE on the device
+        o.plastic_lambert = make_float3(m.diffuse[0] / m.diffuse_probability, m.diffuse[1] / m.diffuse_probability, m.diffuse[2] / m.diffuse_probability);
+        o.plastic_phong = make_float3(m.specular[0] / m.specular_probability, m.specular[1] / m.specular_probability, m.specular[2] / m.specular_probability);
+    }
+    d.n_nondelta_lights = 0;
+    for (int i = 0; i < sc->light_count; ++i)
+    {
+        const kyd_light& l = sc->lights[i];
+        if (l.kind < 0 || l.kind > KYD_LIGHT_ENVIRONMENT) return fail(ctx, KYD_ERR_INVALID, "unknown light kind");
+        DevLight& o = d.lights[i];
+        o.kind = l.kind;
+        o.color = f3(l.color); o.position = f3(l.position); o.direction = f3(l.direction);
+        o.world_radius = l.world_radius;
+        o.shape = l.shape;
+        if (l.kind == KYD_LIGHT_AREA)
+        {
+            if (l.shape < 0 || l.shape >= sc->shape_count) return fail(ctx, KYD_ERR_INVALID, "area light shape index out of range");
+            d.light_shape[i] = convert_shape(sc->shapes[l.shape]);
+        }
+        if (l.kind == KYD_LIGHT_AREA || l.kind == KYD_LIGHT_ENVIRONMENT) d.n_nondelta_lights++;
+    }
+    ctx->has_scene = true;
+    ctx->scene_generation++;
+    return KYD_OK;
+}
+
+int kyd_render(kyd_ctx* ctx, const kyd_render_desc* d, float* film_rgb)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, KYD_ERR_NO_SCENE, "kyd_render before kyd_upload_scene");
+    if (!film_rgb) return fail(ctx, KYD_ERR_INVALID, "film pointer is null");
+    int rc = validate(ctx, d);
+    if (rc != KYD_OK) return rc;
+    if (d->flags & KYD_FLAG_ACCUMULATE) return fail(ctx, KYD_ERR_INVALID, "KYD_FLAG_ACCUMULATE needs kyd_render_device");
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const size_t floats = (size_t)d->width * d->height * 3;
+    if ((rc = ensure_film(ctx, floats)) != KYD_OK) return rc;
+    if ((rc = ensure_pinned(ctx, floats)) != KYD_OK) return rc;
+
+    if ((rc = render_to_device(ctx, d, ctx->film_dev, ctx->stream, true)) != KYD_OK) return rc;
+    KYD_CUDA(ctx, cudaMemcpyAsync(ctx->film_pinned, ctx->film_dev, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KYD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(film_rgb, ctx->film_pinned, floats * sizeof(float));
+    finish_stats(ctx, true);
+    return KYD_OK;
+}
+
+int kyd_render_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_rgb_device, void* cuda_stream)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, KYD_ERR_NO_SCENE, "kyd_render_device before kyd_upload_scene");
+    if (!film_rgb_device) return fail(ctx, KYD_ERR_INVALID, "film pointer is null");
+    int rc = validate(ctx, d);
+    if (rc != KYD_OK) return rc;
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if ((rc = render_to_device(ctx, d, film_rgb_device, stream, true)) != KYD_OK) return rc;
+    if (!cuda_stream)
+    {
+        KYD_CUDA(ctx, cudaStreamSynchronize(stream));
+        finish_stats(ctx, true);
+    }
+    return KYD_OK;
+}
+
+int kyd_clamp_device(kyd_ctx* ctx, float* film_rgb_device, int64_t n, void* cuda_stream)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (!film_rgb_device || n < 0) return fail(ctx, KYD_ERR_INVALID, "bad film pointer / size");
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    if (n > 0) launch_clamp(film_rgb_device, n, stream);
+    KYD_CUDA(ctx, cudaGetLastError());
+    if (!cuda_stream) KYD_CUDA(ctx, cudaStreamSynchronize(stream));
+    return KYD_OK;
+}
+
+int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out)
+{
+    if (!ctx || !out) return KYD_ERR_INVALID;
+    // an asynchronous kyd_render_device leaves the counters in flight: settle them
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    finish_stats(ctx, true);
+    *out = ctx->stats;
+    return KYD_OK;
+}
+
+int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (paths < 0) return fail(ctx, KYD_ERR_INVALID, "wave size must be >= 0");
+    ctx->wave_paths = paths;
+    return KYD_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,898 @@
+// kyd_device.cuh -- device-side building blocks of the sm_100a rendering core.
+//
+// Every function restates, operation by operation, the reference function it cites (reference
+// ky.cpp) under the numerical contract of DESIGN.md:
+//   * FP32 add / mul / div / sqrt are IEEE round-to-nearest and never contracted: this file must be
+//     compiled with -fmad=false -prec-div=true -prec-sqrt=true -ftz=false;
+//   * vec3 normalize multiplies by (float)(1.0 / sqrt((double)|v|^2)) because ky.cpp:314 resolves to
+//     ::sqrt(double);
+//   * float transcendentals are the correctly rounded values: CUDA's double sin/cos/pow/acos (<= 2 ulp
+//     in double, explicit FMAs inside libdevice, not affected by -fmad=false) rounded once to float;
+//   * std::max / std::clamp / operator precedence / argument evaluation order are g++'s.
+// The kernels in kyd_kernels.cu only compose these blocks.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "kyd.h"
+#include "kyd_scene.h"
+
+namespace kyd {
+
+#define KYD_DEV __device__ __forceinline__
+
+// the scene of the context that launched the kernel.  This header is included by exactly one
+// translation unit (kyd_kernels.cu), which therefore owns the symbol.
+__constant__ DevScene c_scene;
+
+// ---- constants (ky.cpp:180-188) --------------------------------------------------------------------
+#define KYD_PI 3.14159274101257324e+00f        /* (float)pi            */
+#define KYD_INV_PI 3.18309873342514038e-01f    /* (float)(1/pi)        */
+#define KYD_2PI (2.f * KYD_PI)
+#define KYD_PI_OVER2 (KYD_PI / 2.f)
+#define KYD_PI_OVER4 (KYD_PI / 4.f)
+#define KYD_INV_2PI (KYD_INV_PI / 2.f)
+#define KYD_FLT_EPSILON 1.1920928955078125e-7f
+#define KYD_SHAPE_EPSILON 0.001f               /* shape_t::epsilon, ky.cpp:1093 */
+#define KYD_INF CUDART_INF_F
+
+// std::max(a, b) = (a < b) ? b : a ; std::clamp
+KYD_DEV float max_std(float a, float b) { return (a < b) ? b : a; }
+KYD_DEV float clamp_std(float v, float lo, float hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
+
+// libm contract
+KYD_DEV float cr_sin(float x) { return __double2float_rn(sin((double)x)); }
+KYD_DEV float cr_cos(float x) { return __double2float_rn(cos((double)x)); }
+KYD_DEV void cr_sincos(float x, float* s, float* c)
+{
+    double ds, dc;
+    sincos((double)x, &ds, &dc);
+    *s = __double2float_rn(ds);
+    *c = __double2float_rn(dc);
+}
+KYD_DEV float cr_acos(float x) { return __double2float_rn(acos((double)x)); }
+KYD_DEV float cr_pow(float x, float y) { return __double2float_rn(pow((double)x, (double)y)); }
+
+// ---- vectors (ky.cpp:226-388) -----------------------------------------------------------------------
+KYD_DEV float3 V3(float x, float y, float z) { return make_float3(x, y, z); }
+KYD_DEV float3 add(float3 a, float3 b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+KYD_DEV float3 sub(float3 a, float3 b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+KYD_DEV float3 mul(float3 a, float s) { return V3(a.x * s, a.y * s, a.z * s); }
+KYD_DEV float3 neg(float3 a) { return V3(-a.x, -a.y, -a.z); }
+KYD_DEV float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+KYD_DEV float msq(float3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+KYD_DEV float mag(float3 a) { return __fsqrt_rn(msq(a)); } // (float)sqrt((double)s) == sqrtf(s)
+KYD_DEV float3 cross(float3 a, float3 v)
+{
+    return V3(a.y * v.z - a.z * v.y, a.z * v.x - a.x * v.z, a.x * v.y - a.y * v.x);
+}
+// ky.cpp:314
+KYD_DEV float rsqrt_ky(float s) { return __double2float_rn(__drcp_rn(__dsqrt_rn((double)s))); }
+KYD_DEV float3 normalize(float3 a) { return mul(a, rsqrt_ky(a.x * a.x + a.y * a.y + a.z * a.z)); }
+KYD_DEV float abs_dot(float3 a, float3 b) { return fabsf(dot(a, b)); }
+KYD_DEV float distance_sq(float3 a, float3 b) { return msq(sub(a, b)); }
+KYD_DEV float distance(float3 a, float3 b) { return mag(sub(a, b)); }
+
+// colors share float3: r,g,b = x,y,z
+KYD_DEV float3 cdiv(float3 a, float s) { return V3(a.x / s, a.y / s, a.z / s); }
+KYD_DEV float3 cmulc(float3 a, float3 b) { return V3(a.x * b.x, a.y * b.y, a.z * b.z); }
+KYD_DEV bool is_black(float3 c) { return (c.x <= 0) && (c.y <= 0) && (c.z <= 0); }
+KYD_DEV float max_component(float3 c)
+{
+    float m = c.x;
+    if (m < c.y) m = c.y;
+    if (m < c.z) m = c.z;
+    return m;
+}
+#define KYD_BLACK make_float3(0.f, 0.f, 0.f)
+
+// frame_t(normal) ky.cpp:537-541, 566-571
+struct Frame { float3 s, t, n; };
+KYD_DEV Frame frame_from_z(float3 normal)
+{
+    Frame f;
+    f.n = normalize(normal);
+    float3 tmp = (fabsf(f.n.x) > 0.99f) ? V3(0, 1, 0) : V3(1, 0, 0);
+    f.t = normalize(cross(f.n, tmp));
+    f.s = normalize(cross(f.t, f.n));
+    return f;
+}
+KYD_DEV float3 to_local(const Frame& f, float3 w) { return V3(dot(f.s, w), dot(f.t, w), dot(f.n, w)); }
+KYD_DEV float3 to_world(const Frame& f, float3 l) { return add(add(mul(f.s, l.x), mul(f.t, l.y)), mul(f.n, l.z)); }
+
+// offset_ray_origin ky.cpp:614-620
+KYD_DEV float3 offset_ray_origin(float3 position, float3 normal, float3 direction)
+{
+    float3 offset = mul(normal, 0.01f); // (float)1e-2
+    if (dot(normal, direction) < 0)
+        offset = neg(offset);
+    return add(position, offset);
+}
+
+// ---- sampling warps ky.cpp:710-808 ---------------------------------------------------------------------
+KYD_DEV float2 concentric_disk_sample(float2 u)
+{
+    float rx = 2.f * u.x - 1, ry = 2.f * u.y - 1;
+    if (rx == 0 && ry == 0)
+        return make_float2(0.f, 0.f);
+    float radius, theta;
+    if (fabsf(rx) > fabsf(ry))
+    {
+        radius = rx;
+        theta = KYD_PI_OVER4 * (ry / rx);
+    }
+    else
+    {
+        radius = ry;
+        theta = KYD_PI_OVER2 - KYD_PI_OVER4 * (rx / ry);
+    }
+    float s, c;
+    cr_sincos(theta, &s, &c);
+    return make_float2(c * radius, s * radius);
+}
+
+KYD_DEV float3 cosine_hemisphere_sample(float2 u)
+{
+    float2 p = concentric_disk_sample(u);
+    float z = __fsqrt_rn(max_std(0.f, 1 - p.x * p.x - p.y * p.y));
+    return V3(p.x, p.y, z);
+}
+
+KYD_DEV float3 uniform_sphere_sample(float2 u)
+{
+    float z = 1 - 2 * u.x;
+    float radius = __fsqrt_rn(max_std(0.f, 1.f - z * z));
+    float phi = 2 * KYD_PI * u.y;
+    float s, c;
+    cr_sincos(phi, &s, &c);
+    return V3(radius * c, radius * s, z);
+}
+
+// ---- sampler: counter-seeded LCG48 / debug sampler ------------------------------------------------------
+KYD_DEV unsigned long long mix64(unsigned long long z)
+{
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 27; z *= 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return z;
+}
+
+#define KYD_LCG_A 0x5DEECE66Dull
+#define KYD_LCG_C 0xBull
+#define KYD_LCG_MASK 0xFFFFFFFFFFFFull
+
+struct Sampler
+{
+    unsigned long long state;
+    bool debug;
+
+    KYD_DEV void start(int kind, unsigned long long seed, int x, int y, int sample_index)
+    {
+        debug = (kind == KYD_SAMPLER_DEBUG);
+        unsigned long long key = (unsigned long long)sample_index | ((unsigned long long)x << 24) | ((unsigned long long)y << 40);
+        state = mix64(seed * 0x9E3779B97F4A7C15ull + key) >> 16;
+    }
+    KYD_DEV float get_float()
+    {
+        if (debug) return 0.5f;
+        state = (state * KYD_LCG_A + KYD_LCG_C) & KYD_LCG_MASK;
+        return (float)(unsigned)(state >> 24) * 0x1p-24f; // 24-bit integer: exact
+    }
+    KYD_DEV float2 get_float2()
+    {
+        float x = get_float();
+        float y = get_float();
+        return make_float2(x, y);
+    }
+    KYD_DEV void skip(int n)
+    {
+        if (debug) return;
+        for (int i = 0; i < n; ++i)
+            state = (state * KYD_LCG_A + KYD_LCG_C) & KYD_LCG_MASK;
+    }
+};
+
+// patch P5 of oracle/ref/build_ref.sh: stateless plastic lobe draw
+KYD_DEV float plastic_random(float3 p, float3 wo)
+{
+    unsigned long long h = mix64((unsigned long long)__float_as_uint(wo.y) | ((unsigned long long)__float_as_uint(wo.z) << 32));
+    h = mix64(((unsigned long long)__float_as_uint(p.z) | ((unsigned long long)__float_as_uint(wo.x) << 32)) ^ h);
+    h = mix64(((unsigned long long)__float_as_uint(p.x) | ((unsigned long long)__float_as_uint(p.y) << 32)) ^ h);
+    return (float)(unsigned)(h >> 40) * 0x1p-24f;
+}
+
+// ---- shapes ky.cpp:1009-1519 ------------------------------------------------------------------------------
+struct Ray { float3 o, d; float tmax; };
+struct HitGeom { float3 position, normal, wo; };
+
+KYD_DEV float3 ray_at(const Ray& r, float t) { return add(r.o, mul(r.d, t)); }
+
+KYD_DEV bool is_equal0(float x) // is_equal(x, 0) ky.cpp:213-220
+{
+    float m = 1.f;
+    if (m < fabsf(x)) m = fabsf(x);
+    return fabsf(x - 0.f) <= KYD_FLT_EPSILON * m;
+}
+
+// the hit test of shape_t::intersect WITHOUT filling the isect: returns true and the distance when the
+// shape is hit inside (epsilon, tmax).  The isect is a pure function of (ray, distance, shape) and is
+// filled once for the final hit by shape_hit_geom().
+KYD_DEV bool shape_hit_distance(const DevShape& s, const Ray& r, float tmax, float* out_t)
+{
+    switch (s.kind)
+    {
+    case KYD_SHAPE_SPHERE: // ky.cpp:1365-1383
+    {
+        float3 oc = sub(s.p0, r.o);
+        float neg_b = dot(oc, r.d);
+        float discr = neg_b * neg_b - dot(oc, oc) + s.radius_sq;
+        if (discr >= 0)
+        {
+            float sqrt_discr = __fsqrt_rn(discr);
+            float t = neg_b - sqrt_discr;
+            if (t > KYD_SHAPE_EPSILON && t < tmax) { *out_t = t; return true; }
+            t = neg_b + sqrt_discr;
+            if (t > KYD_SHAPE_EPSILON && t < tmax) { *out_t = t; return true; }
+        }
+        return false;
+    }
+    case KYD_SHAPE_RECTANGLE: // ky.cpp:1265-1285
+    {
+        float3 oa = sub(s.p0, r.o), ob = sub(s.p1, r.o), oc = sub(s.p2, r.o), od = sub(s.p3, r.o);
+        float v0d = dot(cross(oc, ob), r.d);
+        float v1d = dot(cross(ob, oa), r.d);
+        float v2d = dot(cross(oa, od), r.d);
+        float v3d = dot(cross(od, oc), r.d);
+        if (((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f) && (v3d < 0.f)) ||
+            ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f) && (v3d >= 0.f)))
+        {
+            float t = dot(s.n, oa) / dot(s.n, r.d);
+            if ((t > KYD_SHAPE_EPSILON) && (t < tmax)) { *out_t = t; return true; }
+        }
+        return false;
+    }
+    case KYD_SHAPE_TRIANGLE: // ky.cpp:1183-1204
+    {
+        float3 oa = sub(s.p0, r.o), ob = sub(s.p1, r.o), oc = sub(s.p2, r.o);
+        float v0d = dot(cross(oc, ob), r.d);
+        float v1d = dot(cross(ob, oa), r.d);
+        float v2d = dot(cross(oa, oc), r.d);
+        if (((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f)) || ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f)))
+        {
+            float t = dot(s.n, oa) / dot(s.n, r.d);
+            if ((t > KYD_SHAPE_EPSILON) && (t < tmax)) { *out_t = t; return true; }
+        }
+        return false;
+    }
+    default: // disk ky.cpp:1113-1128
+    {
+        if (is_equal0(dot(r.d, s.n)))
+            return false;
+        float3 op = sub(s.p0, r.o);
+        float t = dot(s.n, op) / dot(s.n, r.d);
+        if ((t > KYD_SHAPE_EPSILON) && (t < tmax))
+        {
+            float3 p = ray_at(r, t);
+            if (distance(s.p0, p) <= s.radius) { *out_t = t; return true; }
+        }
+        return false;
+    }
+    }
+}
+
+// the isect_t a shape builds for a hit at distance t (ky.cpp:1125, 1208, 1288-1290, 1388-1389)
+KYD_DEV HitGeom shape_hit_geom(const DevShape& s, const Ray& r, float t)
+{
+    HitGeom g;
+    g.position = ray_at(r, t);
+    g.wo = neg(r.d);
+    switch (s.kind)
+    {
+    case KYD_SHAPE_SPHERE: g.normal = normalize(sub(g.position, s.p0)); break;
+    case KYD_SHAPE_RECTANGLE: g.normal = dot(s.n, r.d) <= 0 ? s.n : neg(s.n); break;
+    default: g.normal = s.n; break;
+    }
+    return g;
+}
+
+// shape_t::sample_position ky.cpp:1144, 1225, 1307, 1404
+KYD_DEV void shape_sample_position(const DevShape& s, float2 u, float3* lp, float3* ln, float* area_pdf)
+{
+    switch (s.kind)
+    {
+    case KYD_SHAPE_SPHERE:
+    {
+        float3 direction = uniform_sphere_sample(u);
+        *lp = add(s.p0, mul(direction, s.radius));
+        *ln = normalize(direction);
+        break;
+    }
+    case KYD_SHAPE_RECTANGLE:
+        *lp = add(add(s.p1, mul(sub(s.p0, s.p1), u.x)), mul(sub(s.p2, s.p1), u.y));
+        *ln = normalize(s.n);
+        break;
+    case KYD_SHAPE_TRIANGLE:
+    {
+        float su0 = __fsqrt_rn(u.x);
+        float bx = 1 - su0, by = u.y * su0;
+        *lp = add(add(mul(s.p0, bx), mul(s.p1, by)), mul(s.p2, 1 - bx - by));
+        *ln = s.n;
+        break;
+    }
+    default:
+    {
+        Frame f = frame_from_z(s.n);
+        float2 sp = concentric_disk_sample(u);
+        *lp = add(s.p0, mul(add(mul(f.s, sp.x), mul(f.t, sp.y)), s.radius));
+        *ln = normalize(s.n);
+        break;
+    }
+    }
+    *area_pdf = 1 / s.area;
+}
+
+// shape_t::sample_direction ky.cpp:1028-1051 and sphere_t's override ky.cpp:1419-1501
+KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade, float2 u, float3* lp, float3* ln, float* pdf)
+{
+    if (s.kind == KYD_SHAPE_SPHERE)
+    {
+        float3 center = s.p0;
+        float radius = s.radius;
+        if (distance_sq(p, center) <= radius * radius)
+        {
+            float area_pdf;
+            shape_sample_position(s, u, lp, ln, &area_pdf);
+            float3 wi = sub(*lp, p);
+            if (msq(wi) == 0)
+                *pdf = 0;
+            else
+            {
+                wi = normalize(wi);
+                *pdf = area_pdf * distance_sq(*lp, p) / abs_dot(n_shade, neg(wi));
+            }
+            if (isinf(*pdf))
+                *pdf = 0.f;
+            return;
+        }
+
+        float dist = distance(p, center);
+        float inv_dist = 1 / dist;
+        float sin_theta_max = radius * inv_dist;
+        float sin_theta_max_sq = sin_theta_max * sin_theta_max;
+        float inv_sin_theta_max = 1 / sin_theta_max;
+        float cos_theta_max = __fsqrt_rn(max_std(0.f, 1 - sin_theta_max_sq));
+
+        float cos_theta = (cos_theta_max - 1) * u.x + 1;
+        float sin_theta_sq = 1 - cos_theta * cos_theta;
+        if (sin_theta_max_sq < 0.00068523f)
+        {
+            sin_theta_sq = sin_theta_max_sq * u.x;
+            cos_theta = __fsqrt_rn(1 - sin_theta_sq);
+        }
+
+        float cos_alpha = sin_theta_sq * inv_sin_theta_max +
+            cos_theta * __fsqrt_rn(max_std(0.f, 1.f - sin_theta_sq * inv_sin_theta_max * inv_sin_theta_max));
+        float sin_alpha = __fsqrt_rn(max_std(0.f, 1.f - cos_alpha * cos_alpha));
+        float phi = u.y * 2 * KYD_PI;
+
+        float3 normal = mul(sub(center, p), inv_dist);
+        Frame f = frame_from_z(normal);
+
+        float sp, cp;
+        cr_sincos(phi, &sp, &cp);
+        float3 wn = add(add(mul(neg(f.s), sin_alpha * cp), mul(neg(f.t), sin_alpha * sp)), mul(neg(f.n), cos_alpha));
+        *lp = add(center, mul(wn, radius));
+        *ln = wn;
+        *pdf = 1 / (2 * KYD_PI * (1 - cos_theta_max));
+        return;
+    }
+
+    float area_pdf;
+    shape_sample_position(s, u, lp, ln, &area_pdf);
+    float3 wi = sub(*lp, p);
+    if (msq(wi) == 0)
+        *pdf = 0;
+    else
+    {
+        wi = normalize(wi);
+        *pdf = area_pdf * distance_sq(*lp, p) / abs_dot(*ln, neg(wi));
+        if (isinf(*pdf))
+            *pdf = 0.f;
+    }
+}
+
+// shape_t::pdf_direction ky.cpp:1055-1090 and sphere_t's override ky.cpp:1503-1513
+KYD_DEV float shape_pdf_direction(const DevShape& s, float3 p, float3 n_shade, float3 wi)
+{
+    if (s.kind == KYD_SHAPE_SPHERE)
+    {
+        if (!(distance_sq(p, s.p0) <= s.radius * s.radius))
+        {
+            float sin_theta_max_sq = s.radius * s.radius / distance_sq(p, s.p0);
+            float cos_theta_max = __fsqrt_rn(max_std(0.f, 1 - sin_theta_max_sq));
+            return 1 / (2 * KYD_PI * (1 - cos_theta_max));
+        }
+    }
+    Ray r;
+    r.o = offset_ray_origin(p, n_shade, wi);
+    r.d = wi;
+    r.tmax = KYD_INF;
+    float t;
+    if (!shape_hit_distance(s, r, r.tmax, &t))
+        return 0.f;
+    HitGeom g = shape_hit_geom(s, r, t);
+    float pdf = distance_sq(p, g.position) / (abs_dot(g.normal, neg(wi)) * s.area);
+    if (isinf(pdf))
+        pdf = 0.f;
+    return pdf;
+}
+
+// ---- BSDFs ky.cpp:1918-2555, materials ky.cpp:2579-2682 -----------------------------------------------------
+enum { LOBE_LAMBERT = 0, LOBE_MIRROR = 1, LOBE_FRESNEL = 2, LOBE_PHONG = 3 };
+enum { BSDF_REFLECTION = 1, BSDF_TRANSMISSION = 2, BSDF_DIFFUSE = 4, BSDF_GLOSSY = 8, BSDF_SPECULAR = 16 };
+
+struct Bsdf
+{
+    Frame f;
+    float3 a;       // lambert albedo / mirror + fresnel reflectance / phong specular reflectance
+    float3 t;       // fresnel transmittance
+    float eta_t;    // eta_i is 1 (ky.cpp:2630)
+    float exponent;
+    int lobe;
+};
+
+struct BsdfSample { float3 f, wi; float pdf; int type; };
+
+KYD_DEV bool bsdf_is_delta(int lobe) { return lobe == LOBE_MIRROR || lobe == LOBE_FRESNEL; }
+KYD_DEV bool same_hemisphere(float3 w, float3 wp) { return w.z * wp.z > 0; }
+
+KYD_DEV float3 reflect_z(float3 wo) // reflect(wo, (0,0,1)) ky.cpp:1923-1928
+{
+    float3 n = V3(0, 0, 1);
+    return add(neg(wo), mul(n, 2 * dot(wo, n)));
+}
+
+KYD_DEV float fresnel_dielectric(float cos_theta_i, float eta_i, float eta_t) // ky.cpp:1963-1996
+{
+    cos_theta_i = clamp_std(cos_theta_i, -1.f, 1.f);
+    if (!(cos_theta_i > 0.f))
+    {
+        float tmp = eta_i; eta_i = eta_t; eta_t = tmp;
+        cos_theta_i = fabsf(cos_theta_i);
+    }
+    float sin_theta_i = __fsqrt_rn(max_std(0.f, 1 - cos_theta_i * cos_theta_i));
+    float sin_theta_t = eta_i / eta_t * sin_theta_i;
+    if (sin_theta_t >= 1)
+        return 1;
+    float cos_theta_t = __fsqrt_rn(max_std(0.f, 1 - sin_theta_t * sin_theta_t));
+    float r_para = ((eta_t * cos_theta_i) - (eta_i * cos_theta_t)) / ((eta_t * cos_theta_i) + (eta_i * cos_theta_t));
+    float r_perp = ((eta_i * cos_theta_i) - (eta_t * cos_theta_t)) / ((eta_i * cos_theta_i) + (eta_t * cos_theta_t));
+    return (r_para * r_para + r_perp * r_perp) / 2;
+}
+
+KYD_DEV bool refract(float3 wi, float3 normal, float eta_ratio, float3* wt) // ky.cpp:1931-1957
+{
+    float cos_theta_i = dot(normal, wi);
+    float sin_theta_i_sq = max_std(0.f, 1 - cos_theta_i * cos_theta_i);
+    float sin_theta_t_sq = eta_ratio * eta_ratio * sin_theta_i_sq;
+    if (sin_theta_t_sq >= 1)
+        return false;
+    float cos_theta_t = __fsqrt_rn(1 - sin_theta_t_sq);
+    *wt = add(mul(neg(wi), eta_ratio), mul(normal, eta_ratio * cos_theta_i - cos_theta_t));
+    return true;
+}
+
+KYD_DEV float3 bsdf_eval_local(const Bsdf& b, float3 wo, float3 wi) // ky.cpp:2227, 2289, 2352, 2489
+{
+    if (b.lobe == LOBE_LAMBERT)
+    {
+        if (!same_hemisphere(wo, wi))
+            return KYD_BLACK;
+        return mul(b.a, KYD_INV_PI);
+    }
+    if (b.lobe == LOBE_PHONG)
+    {
+        if (!same_hemisphere(wo, wi))
+            return KYD_BLACK;
+        float3 wr = reflect_z(wo);
+        float cos_alpha = dot(wr, wi);
+        float3 rho = mul(mul(b.a, b.exponent + 2.f), KYD_INV_2PI);
+        return mul(rho, cr_pow(cos_alpha, b.exponent));
+    }
+    return KYD_BLACK;
+}
+
+KYD_DEV float bsdf_pdf_local(const Bsdf& b, float3 wo, float3 wi) // ky.cpp:2237, 2290, 2353, 2502
+{
+    if (b.lobe == LOBE_LAMBERT)
+        return same_hemisphere(wo, wi) ? fabsf(wi.z) * KYD_INV_PI : 0;
+    if (b.lobe == LOBE_PHONG)
+    {
+        float3 wr = reflect_z(wo);
+        float cos_theta = max_std(0.f, dot(wr, wi));
+        return (b.exponent + 1.f) * cr_pow(cos_theta, b.exponent) * KYD_INV_2PI;
+    }
+    return 0;
+}
+
+// phong eval_ and pdf_ of the same (wo, wi) share one pow(): both raise to the same exponent and
+// max(0, c) differs from c only where pow's result is unused or c < 0
+KYD_DEV void bsdf_eval_pdf_local(const Bsdf& b, float3 wo, float3 wi, float3* f, float* pdf)
+{
+    *f = bsdf_eval_local(b, wo, wi);
+    *pdf = bsdf_pdf_local(b, wo, wi);
+}
+
+KYD_DEV float3 bsdf_eval(const Bsdf& b, float3 world_wo, float3 world_wi) // ky.cpp:2162
+{
+    return bsdf_eval_local(b, to_local(b.f, world_wo), to_local(b.f, world_wi));
+}
+KYD_DEV float bsdf_pdf(const Bsdf& b, float3 world_wo, float3 world_wi) // ky.cpp:2167
+{
+    return bsdf_pdf_local(b, to_local(b.f, world_wo), to_local(b.f, world_wi));
+}
+
+// bsdf_t::sample ky.cpp:2173 with sample_ of ky.cpp:2242, 2292, 2355, 2510
+KYD_DEV BsdfSample bsdf_sample(const Bsdf& b, float3 world_wo, float2 u)
+{
+    BsdfSample s;
+    s.f = KYD_BLACK;
+    s.wi = V3(0, 0, 0);
+    s.pdf = 0;
+    s.type = 0;
+    float3 wo = to_local(b.f, world_wo);
+
+    if (b.lobe == LOBE_LAMBERT)
+    {
+        s.wi = cosine_hemisphere_sample(u);
+        if (wo.z < 0)
+            s.wi.z *= -1;
+        s.f = bsdf_eval_local(b, wo, s.wi);
+        s.pdf = bsdf_pdf_local(b, wo, s.wi);
+        s.type = BSDF_REFLECTION | BSDF_DIFFUSE;
+    }
+    else if (b.lobe == LOBE_MIRROR)
+    {
+        s.wi = V3(-wo.x, -wo.y, wo.z);
+        s.f = cdiv(b.a, fabsf(s.wi.z));
+        s.pdf = 1;
+        s.type = BSDF_REFLECTION | BSDF_SPECULAR;
+    }
+    else if (b.lobe == LOBE_FRESNEL)
+    {
+        float reflect_percent = fresnel_dielectric(wo.z, 1.f, b.eta_t);
+        float refract_percent = 1 - reflect_percent;
+        if (u.x < reflect_percent)
+        {
+            s.wi = V3(-wo.x, -wo.y, wo.z);
+            s.pdf = reflect_percent;
+            s.f = cdiv(mul(b.a, reflect_percent), fabsf(s.wi.z));
+            s.type = BSDF_REFLECTION | BSDF_SPECULAR;
+        }
+        else
+        {
+            float3 normal = V3(0, 0, 1);
+            bool into = dot(normal, wo) > 0;
+            float3 wo_normal = into ? normal : mul(normal, -1.f);
+            float eta = into ? 1.f / b.eta_t : b.eta_t / 1.f;
+            if (refract(wo, wo_normal, eta, &s.wi))
+            {
+                s.pdf = refract_percent;
+                s.f = cdiv(mul(b.t, refract_percent), fabsf(s.wi.z));
+                s.type = BSDF_TRANSMISSION | BSDF_SPECULAR;
+            }
+        }
+    }
+    else // LOBE_PHONG
+    {
+        float phi = 2.f * KYD_PI * u.x;
+        float cos_theta = cr_pow(u.y, 1.f / (b.exponent + 1.f));
+        float sin_theta = __fsqrt_rn(1.f - cos_theta * cos_theta);
+        float sp, cp;
+        cr_sincos(phi, &sp, &cp);
+        float3 local = V3(cp * sin_theta, sp * sin_theta, cos_theta);
+        Frame fr = frame_from_z(reflect_z(wo));
+        s.wi = to_world(fr, local);
+        if (wo.z < 0)
+            s.wi.z *= -1;
+        s.f = bsdf_eval_local(b, wo, s.wi);
+        s.pdf = bsdf_pdf_local(b, wo, s.wi);
+        s.type = BSDF_REFLECTION | BSDF_GLOSSY;
+    }
+
+    s.wi = to_world(b.f, s.wi);
+    return s;
+}
+
+// material_t::scattering ky.cpp:2587, 2604, 2628, 2661
+KYD_DEV void material_scattering(const DevMaterial& m, const HitGeom& g, Bsdf* b)
+{
+    b->f = frame_from_z(g.normal);
+    b->t = KYD_BLACK;
+    b->eta_t = 1.f;
+    b->exponent = 0.f;
+    if (m.kind == KYD_MAT_MATTE)
+    {
+        b->lobe = LOBE_LAMBERT;
+        b->a = m.diffuse;
+    }
+    else if (m.kind == KYD_MAT_MIRROR)
+    {
+        b->lobe = LOBE_MIRROR;
+        b->a = m.specular;
+    }
+    else if (m.kind == KYD_MAT_GLASS)
+    {
+        b->lobe = LOBE_FRESNEL;
+        b->eta_t = m.eta;
+        b->a = m.specular;
+        b->t = m.transmission;
+    }
+    else
+    {
+        float random = plastic_random(g.position, g.wo);
+        if (random < m.p_specular)
+        {
+            b->lobe = LOBE_PHONG;
+            b->a = m.plastic_phong;
+            b->exponent = m.exponent;
+        }
+        else
+        {
+            b->lobe = LOBE_LAMBERT;
+            b->a = m.plastic_lambert;
+        }
+    }
+}
+
+// ---- scene traversal ky.cpp:3077-3088, 3172-3206 ------------------------------------------------------------
+
+// closest hit over all surfaces in list order (strict t < tmax keeps the first of equal distances)
+KYD_DEV int scene_closest(const Ray& r, float* out_t)
+{
+    float tmax = r.tmax;
+    int best = -1;
+    const int n = c_scene.n_surfaces;
+    for (int i = 0; i < n; ++i)
+    {
+        float t;
+        if (shape_hit_distance(c_scene.surf_shape[i], r, tmax, &t))
+        {
+            tmax = t;
+            best = i;
+        }
+    }
+    *out_t = tmax;
+    return best;
+}
+
+KYD_DEV bool scene_any_hit(const Ray& r)
+{
+    const int n = c_scene.n_surfaces;
+    for (int i = 0; i < n; ++i)
+    {
+        float t;
+        if (shape_hit_distance(c_scene.surf_shape[i], r, r.tmax, &t))
+            return true;
+    }
+    return false;
+}
+
+KYD_DEV float3 areal_radiance(const DevLight& l, float3 light_normal, float3 wo) // ky.cpp:2957-2960
+{
+    return (dot(light_normal, wo) > 0) ? l.color : KYD_BLACK;
+}
+
+KYD_DEV float3 surface_emission(int surface, const HitGeom& g) // ky.cpp:3084
+{
+    int li = c_scene.surf_light[surface];
+    return li >= 0 ? areal_radiance(c_scene.lights[li], g.normal, g.wo) : KYD_BLACK;
+}
+
+KYD_DEV float3 environment_lighting() // ky.cpp:3231-3237
+{
+    return c_scene.env_light >= 0 ? c_scene.lights[c_scene.env_light].color : KYD_BLACK;
+}
+
+// scene_t::occluded(isect, point) ky.cpp:3187-3201: the shadow ray
+KYD_DEV Ray shadow_ray(const HitGeom& from, float3 target)
+{
+    float3 direction = normalize(sub(target, from.position));
+    float dist = distance(from.position, target);
+    Ray r;
+    r.o = offset_ray_origin(from.position, from.normal, direction);
+    r.d = direction;
+    r.tmax = dist - 2e-3f;
+    return r;
+}
+
+KYD_DEV Ray spawn_ray(const HitGeom& g, float3 direction) // ky.cpp:665-668
+{
+    Ray r;
+    r.o = offset_ray_origin(g.position, g.normal, direction);
+    r.d = direction;
+    r.tmax = KYD_INF;
+    return r;
+}
+
+// ---- lights ky.cpp:2810-3062 ----------------------------------------------------------------------------------
+struct LightSample { float3 position, wi; float pdf; float3 Li; };
+
+KYD_DEV bool light_is_delta(int kind) { return kind == KYD_LIGHT_POINT || kind == KYD_LIGHT_DIRECTION; }
+KYD_DEV float spherical_theta(float3 v) { return cr_acos(clamp_std(v.z, -1.f, 1.f)); } // ky.cpp:410
+
+KYD_DEV LightSample light_sample_Li(int light_index, const HitGeom& g, float2 u)
+{
+    const DevLight& l = c_scene.lights[light_index];
+    LightSample s;
+    s.position = V3(0, 0, 0);
+    s.wi = V3(0, 0, 0);
+    s.pdf = 0;
+    s.Li = KYD_BLACK;
+    if (l.kind == KYD_LIGHT_POINT) // ky.cpp:2825-2853
+    {
+        s.position = l.position;
+        s.wi = normalize(sub(l.position, g.position));
+        s.pdf = 1.f;
+        s.Li = cdiv(l.color, distance_sq(l.position, g.position));
+    }
+    else if (l.kind == KYD_LIGHT_DIRECTION) // ky.cpp:2891-2901
+    {
+        s.wi = neg(l.direction);
+        s.position = add(g.position, mul(mul(s.wi, 2.f), l.world_radius));
+        s.pdf = 1;
+        s.Li = l.color;
+    }
+    else if (l.kind == KYD_LIGHT_AREA) // ky.cpp:2964-2981
+    {
+        float3 lp, ln;
+        shape_sample_direction(c_scene.light_shape[light_index], g.position, g.normal, u, &lp, &ln, &s.pdf);
+        s.position = lp;
+        if (!(s.pdf == 0 || msq(sub(lp, g.position)) == 0))
+        {
+            s.wi = normalize(sub(lp, g.position));
+            s.Li = areal_radiance(l, ln, neg(s.wi));
+        }
+    }
+    else // environment ky.cpp:3026-3041
+    {
+        s.wi = uniform_sphere_sample(u);
+        s.position = add(g.position, mul(mul(s.wi, 2.f), l.world_radius));
+        float sin_theta = cr_sin(spherical_theta(s.wi));
+        s.pdf = 1 / (2 * KYD_PI * KYD_PI * sin_theta);
+        if (sin_theta == 0)
+            s.pdf = 0;
+        s.Li = l.color;
+    }
+    return s;
+}
+
+KYD_DEV float light_pdf_Li(int light_index, const HitGeom& g, float3 wi)
+{
+    const DevLight& l = c_scene.lights[light_index];
+    if (l.kind == KYD_LIGHT_AREA) // ky.cpp:2984-2988
+        return shape_pdf_direction(c_scene.light_shape[light_index], g.position, g.normal, wi);
+    if (l.kind == KYD_LIGHT_ENVIRONMENT) // ky.cpp:3043-3053
+    {
+        float sin_theta = cr_sin(spherical_theta(wi));
+        if (sin_theta == 0)
+            return 0;
+        return 1 / (2 * KYD_PI * KYD_PI * sin_theta);
+    }
+    return 0;
+}
+
+// ---- direct lighting ky.cpp:3834-4088 ---------------------------------------------------------------------------
+// Each estimator is split in two halves so that the ray query in the middle can be a separate
+// wavefront stage: *_setup() computes the ray and the value the estimator returns IF the ray sees what
+// it has to see (everything in the reference after the query is a pure function of data known before
+// it, because areal_radiance is either the light's radiance or black); *_resolve() applies the query.
+
+struct NeeRay
+{
+    Ray ray;        // tmax = inf: closest-hit query (BSDF-sampled); finite: occlusion query (light-sampled)
+    float3 value;   // contribution if the query succeeds
+    int light;      // closest-hit query: the light the hit surface must carry (or be missed for the environment light)
+    bool active;    // the query can change the result and has to be traced
+    bool ref_query; // the reference issues this scene query (it traces before it knows the result is black)
+};
+
+// BSDF-sampled half: estimate_direct_lighting_by_bsdf (ky.cpp:3889-3930) when mis == false,
+// estimate_direct_lighting_by_bsdf_mis (ky.cpp:3968-4033) when mis == true
+KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, float2 random_bsdf, bool mis)
+{
+    NeeRay q;
+    q.active = false;
+    q.ref_query = false;
+    q.light = light_index;
+    q.value = KYD_BLACK;
+    const DevLight& l = c_scene.lights[light_index];
+    if (bsdf_is_delta(b.lobe) || light_is_delta(l.kind))
+        return q;
+    BsdfSample bs = bsdf_sample(b, g.wo, random_bsdf);
+    float3 f_cos = mul(bs.f, abs_dot(bs.wi, g.normal));
+    if (is_black(f_cos) || (mis ? (bs.pdf <= 0) : (bs.pdf == 0)))
+        return q;
+    q.ref_query = true;
+    q.ray = spawn_ray(g, bs.wi);
+    // Li is the light's radiance when the query succeeds (area: one-sided test in nee_bsdf_resolve)
+    float3 Li = l.color;
+    if (is_black(Li))
+        return q;
+    if (!mis)
+        q.value = cdiv(cmulc(f_cos, Li), bs.pdf);
+    else
+    {
+        float light_pdf = light_pdf_Li(light_index, g, bs.wi);
+        if (!(light_pdf > 0))
+            return q;
+        q.value = cdiv(mul(cmulc(f_cos, Li), 2.f), bs.pdf + light_pdf);
+    }
+    q.active = true;
+    return q;
+}
+
+// ky.cpp:3905-3919 / 3987-4001: what the BSDF-sampled ray found
+KYD_DEV float3 nee_bsdf_resolve(const NeeRay& q, int hit_surface, float hit_t)
+{
+    const DevLight& l = c_scene.lights[q.light];
+    if (hit_surface >= 0)
+    {
+        if (c_scene.surf_light[hit_surface] != q.light)
+            return KYD_BLACK;
+        // emission of the hit: areal_radiance(light_isect, light_isect.wo) with the hit's normal
+        HitGeom lg = shape_hit_geom(c_scene.surf_shape[hit_surface], q.ray, hit_t);
+        return (dot(lg.normal, lg.wo) > 0) ? q.value : KYD_BLACK;
+    }
+    return l.kind == KYD_LIGHT_ENVIRONMENT ? q.value : KYD_BLACK;
+}
+
+// light-sampled half: estimate_direct_lighting_by_emitter (ky.cpp:3933-3962) when mis == false,
+// estimate_direct_lighting_by_emitter_mis (ky.cpp:4035-4074) when mis == true
+KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index, float2 random_light, bool mis)
+{
+    NeeRay q;
+    q.active = false;
+    q.ref_query = false;
+    q.light = light_index;
+    q.value = KYD_BLACK;
+    const DevLight& l = c_scene.lights[light_index];
+    if (bsdf_is_delta(b.lobe))
+        return q;
+    LightSample ls = light_sample_Li(light_index, g, random_light);
+    if (is_black(ls.Li) || (mis ? (ls.pdf <= 0) : (ls.pdf == 0)))
+        return q;
+    q.ref_query = true;
+    q.ray = shadow_ray(g, ls.position);
+    float3 wo_l = to_local(b.f, g.wo), wi_l = to_local(b.f, ls.wi);
+    float3 f_cos = mul(bsdf_eval_local(b, wo_l, wi_l), abs_dot(ls.wi, g.normal));
+    if (is_black(f_cos))
+        return q;
+    if (!mis || light_is_delta(l.kind))
+        q.value = cdiv(cmulc(f_cos, ls.Li), ls.pdf);
+    else
+    {
+        float bsdf_pdf_v = bsdf_pdf_local(b, wo_l, wi_l);
+        q.value = cdiv(mul(cmulc(f_cos, ls.Li), 2.f), ls.pdf + bsdf_pdf_v);
+    }
+    q.active = true;
+    return q;
+}
+
+// camera_t::generate_ray ky.cpp:1884-1892 (+ origin push of smallpt_rewrite.cpp:676)
+KYD_DEV Ray generate_ray(float px, float py)
+{
+    const DevCamera& cam = c_scene.camera;
+    float3 direction = add(add(cam.front, mul(cam.right, px / cam.res_x - 0.5f)), mul(cam.up, 0.5f - py / cam.res_y));
+    Ray r;
+    r.o = cam.position;
+    if (cam.push != 0)
+        r.o = add(r.o, mul(direction, cam.push));
+    r.d = normalize(direction);
+    r.tmax = KYD_INF;
+    return r;
+}
+
+} // namespace kyd

@@ -1,0 +1,392 @@
+// kyd_kernels.cu -- sm_100a kernels of the rendering core: the per-pixel path (all integrators) and
+// the clamp kernel.  The wavefront stages live in kyd_wavefront.cu.
+//
+// Compile with -fmad=false (see kyd_device.cuh).
+#include "kyd_internal.h"
+#include "kyd_device.cuh"
+
+namespace kyd {
+
+void upload_scene_constant(const DevScene& scene, cudaStream_t stream)
+{
+    cudaMemcpyToSymbolAsync(c_scene, &scene, sizeof(DevScene), 0, cudaMemcpyHostToDevice, stream);
+}
+
+// ---- integrators as per-thread loops -----------------------------------------------------------------
+struct Counters { unsigned rays, traced; };
+
+struct Isect
+{
+    HitGeom g;
+    Bsdf b;
+    float3 emission;
+    int surface;
+};
+
+// scene_t::intersect + surface_t::intersect ky.cpp:3172-3184, 3077-3088
+KYD_DEV bool scene_intersect(const Ray& r, Isect& is, Counters& c)
+{
+    c.rays++;
+    c.traced++;
+    float t;
+    int s = scene_closest(r, &t);
+    if (s < 0)
+        return false;
+    is.surface = s;
+    is.g = shape_hit_geom(c_scene.surf_shape[s], r, t);
+    material_scattering(c_scene.materials[c_scene.surf_material[s]], is.g, &is.b);
+    is.emission = surface_emission(s, is.g);
+    return true;
+}
+
+// emission seen along a ray, without building a BSDF (ky.cpp:4345-4349, 4358-4372)
+KYD_DEV float3 trace_emission(const Ray& r, Counters& c)
+{
+    c.rays++;
+    c.traced++;
+    float t;
+    int s = scene_closest(r, &t);
+    if (s < 0)
+        return environment_lighting();
+    HitGeom g = shape_hit_geom(c_scene.surf_shape[s], r, t);
+    return surface_emission(s, g);
+}
+
+KYD_DEV float3 nee_trace(const NeeRay& q, bool closest, Counters& c)
+{
+    if (q.ref_query)
+        c.rays++;
+    if (!q.active)
+        return KYD_BLACK;
+    c.traced++;
+    if (closest)
+    {
+        float t;
+        int s = scene_closest(q.ray, &t);
+        return nee_bsdf_resolve(q, s, t);
+    }
+    return scene_any_hit(q.ray) ? KYD_BLACK : q.value;
+}
+
+// sample_all_light ky.cpp:3834-3872 (g++ draws random_bsdf before random_light)
+KYD_DEV float3 sample_all_light(const HitGeom& g, const Bsdf& b, Sampler& smp, int direct_sample, Counters& c)
+{
+    float3 Ld = KYD_BLACK;
+    const int n = c_scene.n_lights;
+    for (int l = 0; l < n; ++l)
+    {
+        float2 random_bsdf = smp.get_float2();
+        float2 random_light = smp.get_float2();
+        float3 e = KYD_BLACK;
+        switch (direct_sample)
+        {
+        case KYD_DS_BSDF:
+            if (!light_is_delta(c_scene.lights[l].kind))
+                e = nee_trace(nee_bsdf_setup(g, b, l, smp.get_float2(), false), true, c); // a third pair, ky.cpp:3900
+            break;
+        case KYD_DS_LIGHT:
+            e = nee_trace(nee_light_setup(g, b, l, random_light, false), false, c);
+            break;
+        case KYD_DS_BSDF_MIS:
+            e = nee_trace(nee_bsdf_setup(g, b, l, random_bsdf, true), true, c);
+            break;
+        case KYD_DS_LIGHT_MIS:
+            e = nee_trace(nee_light_setup(g, b, l, random_light, true), false, c);
+            break;
+        case KYD_DS_BOTH_MIS: // ky.cpp:4076-4088
+        {
+            float3 Lb = nee_trace(nee_bsdf_setup(g, b, l, random_bsdf, true), true, c);
+            float3 Ll = nee_trace(nee_light_setup(g, b, l, random_light, true), false, c);
+            e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
+            break;
+        }
+        default:
+            break;
+        }
+        Ld = add(Ld, e);
+    }
+    return Ld;
+}
+
+KYD_DEV float3 li_debug(const Ray& r, int integrator, Counters& c) // ky.cpp:4105-4122
+{
+    Isect is;
+    if (scene_intersect(r, is, c))
+    {
+        if (integrator == KYD_INT_POSITION) return normalize(is.g.position);
+        if (integrator == KYD_INT_NORMAL) return normalize(is.g.normal);
+        if (integrator == KYD_INT_BASECOLOR) return bsdf_eval(is.b, is.g.wo, is.g.normal);
+    }
+    return KYD_BLACK;
+}
+
+KYD_DEV float3 li_direct(const Ray& r, Sampler& smp, int direct_sample, Counters& c) // ky.cpp:4136-4154
+{
+    Isect is;
+    if (!scene_intersect(r, is, c))
+        return environment_lighting();
+    float3 Lo = is.emission;
+    if (!bsdf_is_delta(is.b.lobe))
+        Lo = add(Lo, sample_all_light(is.g, is.b, smp, direct_sample, c));
+    return Lo;
+}
+
+KYD_DEV float3 li_path_iteration(Ray r, Sampler& smp, int max_depth, int direct_sample, Counters& c) // ky.cpp:4529-4617
+{
+    float3 Lo = KYD_BLACK;
+    float3 beta = V3(1, 1, 1);
+    bool is_prev_specular = false;
+
+    for (int bounces = 0;; ++bounces)
+    {
+        Isect is;
+        bool hit = scene_intersect(r, is, c);
+
+        if (bounces == 0 || is_prev_specular)
+            Lo = add(Lo, cmulc(beta, hit ? is.emission : environment_lighting()));
+
+        if (!hit || bounces >= max_depth)
+            break;
+
+        if (!bsdf_is_delta(is.b.lobe))
+        {
+            float3 Ld = cmulc(beta, sample_all_light(is.g, is.b, smp, direct_sample, c));
+            Lo = add(Lo, Ld);
+        }
+
+        BsdfSample bs = bsdf_sample(is.b, is.g.wo, smp.get_float2());
+        if (is_black(bs.f) || bs.pdf == 0.f)
+            break;
+
+        beta = cmulc(beta, cdiv(mul(bs.f, abs_dot(bs.wi, is.g.normal)), bs.pdf));
+        is_prev_specular = (bs.type & BSDF_SPECULAR) != 0;
+        r = spawn_ray(is.g, bs.wi);
+
+        if (bounces > 3)
+        {
+            float q = max_std(0.05f, 1 - max_component(beta));
+            if (smp.get_float() < q)
+                break;
+            beta = mul(beta, 1 / (1 - q));
+        }
+    }
+    return Lo;
+}
+
+// ---- the three recursive integrators (ky.cpp:4191-4514) as loops with an explicit stack ----------------
+// A level returns  Lo_level + ((f * Li_deeper) * |cos|) / pdf  (ky.cpp:4233, 4400, 4512): the forward
+// loop records (Lo_level, f, |cos|, pdf) per level and the unwind loop applies the same expression
+// from the deepest level outwards, so the FP32 result is the recursion's.
+struct Level { float3 Lo, f; float a, p; };
+
+// russian roulette shared by the three (ky.cpp:4219-4226, 4389-4397, 4501-4509)
+KYD_DEV bool recursion_roulette(Sampler& smp, int* depth, BsdfSample* bs)
+{
+    if (++*depth > 3)
+    {
+        float m = max_component(bs->f);
+        if (smp.get_float() < m)
+            bs->f = mul(bs->f, 1 / m);
+        else
+            return false;
+    }
+    return true;
+}
+
+KYD_DEV float3 unwind(const Level* stack, int n, float3 result)
+{
+    while (n-- > 0)
+        result = add(stack[n].Lo, cdiv(mul(cmulc(stack[n].f, result), stack[n].a), stack[n].p));
+    return result;
+}
+
+KYD_DEV float3 li_simple_recursion(Ray r, Sampler& smp, int max_depth, Counters& c) // ky.cpp:4201-4237
+{
+    Level stack[KYD_MAX_RECURSION];
+    int n = 0, depth = 0;
+    float3 result;
+    for (;;)
+    {
+        Isect is;
+        if (!scene_intersect(r, is, c)) { result = environment_lighting(); break; }
+        if (depth >= max_depth) { result = is.emission; break; }
+        BsdfSample bs = bsdf_sample(is.b, is.g.wo, smp.get_float2());
+        if (is_black(bs.f) || bs.pdf == 0.f) { result = is.emission; break; }
+        if (!recursion_roulette(smp, &depth, &bs)) { result = is.emission; break; }
+        stack[n].Lo = is.emission;
+        stack[n].f = bs.f;
+        stack[n].a = abs_dot(bs.wi, is.g.normal);
+        stack[n].p = bs.pdf;
+        ++n;
+        r.o = is.g.position; // no origin offset, ky.cpp:4232
+        r.d = bs.wi;
+        r.tmax = KYD_INF;
+    }
+    return unwind(stack, n, result);
+}
+
+// ky.cpp:4321-4401 (deferred == false) and ky.cpp:4440-4513 (deferred == true, with the lighting filter
+// of render_lighting_enum as defined in DESIGN.md)
+template <bool DEFERRED>
+KYD_DEV float3 li_recursion(Ray r, Sampler& smp, int max_depth, int direct_sample, int lighting, Counters& c)
+{
+    Level stack[KYD_MAX_RECURSION];
+    int n = 0, depth = 0;
+    bool prev_specular = false;
+    float3 result;
+    for (;;)
+    {
+        float3 Lo = KYD_BLACK;
+        Isect is;
+        bool hit = scene_intersect(r, is, c);
+
+        if (depth == 0 || (DEFERRED && prev_specular))
+        {
+            float3 Le = hit ? is.emission : environment_lighting();
+            bool keep = !DEFERRED || (depth == 0 ? (lighting & KYD_LIGHTING_EMIT) : (lighting & KYD_LIGHTING_INDIRECT));
+            Lo = add(Lo, keep ? Le : KYD_BLACK);
+        }
+
+        bool recurse = false;
+        if (hit && depth < max_depth)
+        {
+            bool delta = bsdf_is_delta(is.b.lobe);
+            if (!delta)
+            {
+                float3 Ld = sample_all_light(is.g, is.b, smp, direct_sample, c);
+                bool keep = !DEFERRED || (depth == 0 ? (lighting & KYD_LIGHTING_DIRECT) : (lighting & KYD_LIGHTING_INDIRECT));
+                Lo = add(Lo, keep ? Ld : KYD_BLACK);
+            }
+            else if (!DEFERRED)
+            {
+                BsdfSample bs = bsdf_sample(is.b, is.g.wo, smp.get_float2());
+                Ray wi_ray;
+                wi_ray.o = is.g.position; // no origin offset, ky.cpp:4343
+                wi_ray.d = bs.wi;
+                wi_ray.tmax = KYD_INF;
+                float3 Le = trace_emission(wi_ray, c);
+                Lo = add(Lo, cdiv(mul(cmulc(bs.f, Le), abs_dot(bs.wi, is.g.normal)), bs.pdf));
+            }
+
+            BsdfSample bs = bsdf_sample(is.b, is.g.wo, smp.get_float2());
+            int d = depth;
+            if (!(is_black(bs.f) || bs.pdf == 0.f) && recursion_roulette(smp, &d, &bs))
+            {
+                stack[n].Lo = Lo;
+                stack[n].f = bs.f;
+                stack[n].a = abs_dot(bs.wi, is.g.normal);
+                stack[n].p = bs.pdf;
+                ++n;
+                if (DEFERRED)
+                {
+                    r.o = is.g.position; // no origin offset, ky.cpp:4511
+                    r.d = bs.wi;
+                    r.tmax = KYD_INF;
+                }
+                else
+                    r = spawn_ray(is.g, bs.wi); // ky.cpp:4399
+                prev_specular = delta;
+                depth = d;
+                recurse = true;
+            }
+            else
+                Lo = add(Lo, KYD_BLACK); // Lo += color_t{} (ky.cpp:4352, 4462)
+        }
+        if (!recurse) { result = Lo; break; }
+    }
+    return unwind(stack, n, result);
+}
+
+// ---- integrator_t::render ky.cpp:3689-3729: one thread per pixel, samples in order --------------------
+enum { IC_PATH = 0, IC_DIRECT = 1, IC_DEBUG = 2, IC_RECURSION = 3 };
+
+template <int IC>
+__global__ void __launch_bounds__(128) k_render_pixels(RenderParams rp, float* __restrict__ film, DevCounters* __restrict__ counters)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int npix = rp.width * rp.height;
+    Counters cnt = { 0u, 0u };
+    if (idx < npix)
+    {
+        const int x = idx % rp.width, y = idx / rp.width;
+        float3 L = KYD_BLACK;
+        for (int s = rp.sample_begin; s < rp.sample_end; ++s)
+        {
+            Sampler smp;
+            smp.start(rp.sampler, rp.seed, x, y, s);
+            float2 jitter = smp.get_float2(); // get_camera_sample ky.cpp:3714, 971-974
+            Ray r = generate_ray((float)x + jitter.x, (float)y + jitter.y);
+            float3 Li;
+            if (IC == IC_PATH)
+                Li = li_path_iteration(r, smp, rp.max_depth, rp.direct_sample, cnt);
+            else if (IC == IC_DIRECT)
+                Li = li_direct(r, smp, rp.direct_sample, cnt);
+            else if (IC == IC_DEBUG)
+                Li = li_debug(r, rp.integrator, cnt);
+            else
+            {
+                if (rp.integrator == KYD_INT_SIMPLE_PT_RECURSION)
+                    Li = li_simple_recursion(r, smp, rp.max_depth, cnt);
+                else if (rp.integrator == KYD_INT_PT_RECURSION)
+                    Li = li_recursion<false>(r, smp, rp.max_depth, rp.direct_sample, rp.lighting, cnt);
+                else
+                    Li = li_recursion<true>(r, smp, rp.max_depth, rp.direct_sample, rp.lighting, cnt);
+            }
+            L = add(L, mul(Li, rp.weight)); // L = L + Li * (1. / spp), ky.cpp:3717-3721
+        }
+        float* o = film + 3 * (size_t)idx;
+        if (rp.flags & KYD_FLAG_ACCUMULATE)
+            L = add(V3(o[0], o[1], o[2]), L);
+        if (rp.flags & KYD_FLAG_CLAMP)
+            L = V3(clamp_std(L.x, 0.f, 1.f), clamp_std(L.y, 0.f, 1.f), clamp_std(L.z, 0.f, 1.f));
+        o[0] = L.x; o[1] = L.y; o[2] = L.z;
+    }
+    unsigned rays = __reduce_add_sync(0xffffffffu, cnt.rays);
+    unsigned traced = __reduce_add_sync(0xffffffffu, cnt.traced);
+    if ((threadIdx.x & 31) == 0 && (rays | traced))
+    {
+        atomicAdd(&counters->rays, (unsigned long long)rays);
+        atomicAdd(&counters->rays_traced, (unsigned long long)traced);
+    }
+}
+
+void launch_render_pixels(const RenderParams& rp, float* film_dev, DevCounters* counters, cudaStream_t stream)
+{
+    const int npix = rp.width * rp.height;
+    const int block = 128;
+    const int grid = (npix + block - 1) / block;
+    switch (rp.integrator)
+    {
+    case KYD_INT_PT_ITERATION:
+        k_render_pixels<IC_PATH><<<grid, block, 0, stream>>>(rp, film_dev, counters);
+        break;
+    case KYD_INT_DIRECT_LIGHTING:
+        k_render_pixels<IC_DIRECT><<<grid, block, 0, stream>>>(rp, film_dev, counters);
+        break;
+    case KYD_INT_POSITION:
+    case KYD_INT_NORMAL:
+    case KYD_INT_BASECOLOR:
+        k_render_pixels<IC_DEBUG><<<grid, block, 0, stream>>>(rp, film_dev, counters);
+        break;
+    default:
+        k_render_pixels<IC_RECURSION><<<grid, block, 0, stream>>>(rp, film_dev, counters);
+        break;
+    }
+}
+
+__global__ void k_clamp(float* __restrict__ film, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        film[i] = clamp_std(film[i], 0.f, 1.f);
+}
+
+void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream)
+{
+    const int block = 256;
+    k_clamp<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(film_dev, n);
+}
+
+void free_wave_buffers(WaveBuffers&) {}
+
+} // namespace kyd

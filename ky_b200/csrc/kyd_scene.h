@@ -1,0 +1,70 @@
+// kyd_scene.h -- PODs shared by the host side (kyd_api.cu) and the device side (kyd_kernels.cu):
+// the flattened scene as it sits in constant memory, and the per-launch render parameters.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kyd.h"
+
+namespace kyd {
+
+// deepest max_depth the stack-based recursive integrators accept
+#define KYD_MAX_RECURSION 32
+
+// ---- flattened scene in constant memory ---------------------------------------------------------
+struct DevShape
+{
+    float3 p0, p1, p2, p3, n; // meaning per kind as in kyd_shape
+    float radius, radius_sq, area;
+    int kind;
+};
+
+struct DevMaterial
+{
+    int kind;
+    float3 diffuse, specular, transmission;
+    float eta, exponent, p_diffuse, p_specular;
+    float3 plastic_lambert; // diffuse / p_diffuse  (ky.cpp:2670), three IEEE divisions done at upload
+    float3 plastic_phong;   // specular / p_specular (ky.cpp:2666)
+};
+
+struct DevLight
+{
+    int kind;
+    float3 color, position, direction;
+    float world_radius;
+    int shape;
+};
+
+struct DevCamera
+{
+    float3 position, front, right, up;
+    float res_x, res_y, push;
+};
+
+struct DevScene
+{
+    DevCamera camera;
+    int n_surfaces, n_lights, env_light;
+    int n_nondelta_lights;
+    DevShape surf_shape[KYD_MAX_SURFACES];  // geometry of surface i, copied from its shape: traversal order
+    int surf_material[KYD_MAX_SURFACES];
+    int surf_light[KYD_MAX_SURFACES];
+    DevMaterial materials[KYD_MAX_MATERIALS];
+    DevLight lights[KYD_MAX_LIGHTS];
+    DevShape light_shape[KYD_MAX_LIGHTS];   // area_light_t::shape_, independent of the surface list
+};
+
+struct RenderParams
+{
+    int width, height;
+    int spp;
+    int sample_begin, sample_end;
+    int integrator, max_depth, direct_sample, lighting, sampler;
+    unsigned long long seed;
+    unsigned flags;
+    float weight; // (float)(1.0 / spp), ky.cpp:3717
+};
+
+} // namespace kyd
