@@ -187,6 +187,29 @@ def render_desc(width, height, spp, integrator=INT_PT_ITERATION, max_depth=5, di
                       lighting, sampler, seed, flags, 0)
 
 
+def describe_shape(kind, params):
+    """kyd_shape of a shape built by the host classes' constructor (include/ky.hpp)."""
+    p = np.ascontiguousarray(params, np.float32)
+    out = Shape()
+    if host().ky_host_shape_describe(C.c_int(kind), p.ctypes.data_as(C.c_void_p), C.byref(out)) != 0:
+        raise RuntimeError(host().ky_host_last_error().decode())
+    return out
+
+
+def describe_material(kind, params):
+    p = np.ascontiguousarray(params, np.float32)
+    out = Material()
+    if host().ky_host_material_describe(C.c_int(kind), p.ctypes.data_as(C.c_void_p), C.byref(out)) != 0:
+        raise RuntimeError(host().ky_host_last_error().decode())
+    return out
+
+
+def host_sampler_floats(seed, x, y, sample_index, n):
+    out = np.zeros(n, np.float32)
+    host().ky_host_sampler_floats(C.c_uint64(seed), C.c_int(x), C.c_int(y), C.c_int(sample_index), C.c_int(n), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 class Device:
     """One kyd context (one CUDA device, one stream)."""
 

@@ -42,6 +42,68 @@ const kyd_scene_desc* ky_host_scene_desc(void* handle) { return &static_cast<fla
 
 void ky_host_scene_destroy(void* handle) { delete static_cast<flat_scene_t*>(handle); }
 
+// describes one shape / material built through the host classes' constructors (tests: constructor
+// arithmetic -- stored normals, areas, plastic lobe probabilities -- against the reference's)
+// shape params: sphere {c.xyz, r}; rectangle {p0,p1,p2,p3, flip}; triangle {p0,p1,p2, flip}; disk {p, n, r}
+int ky_host_shape_describe(int kind, const float* p, kyd_shape* out)
+{
+    try
+    {
+        std::unique_ptr<shape_t> s;
+        switch (kind)
+        {
+        case KYD_SHAPE_SPHERE: s = std::make_unique<sphere_t>(vec3_t(p[0], p[1], p[2]), p[3]); break;
+        case KYD_SHAPE_RECTANGLE: s = std::make_unique<rectangle_t>(point3_t(p[0], p[1], p[2]), point3_t(p[3], p[4], p[5]), point3_t(p[6], p[7], p[8]), point3_t(p[9], p[10], p[11]), p[12] != 0); break;
+        case KYD_SHAPE_TRIANGLE: s = std::make_unique<triangle_t>(point3_t(p[0], p[1], p[2]), point3_t(p[3], p[4], p[5]), point3_t(p[6], p[7], p[8]), p[9] != 0); break;
+        case KYD_SHAPE_DISK: s = std::make_unique<disk_t>(point3_t(p[0], p[1], p[2]), vec3_t(p[3], p[4], p[5]), p[6]); break;
+        default: throw std::runtime_error("unknown shape kind");
+        }
+        *out = s->describe();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+// material params: {diffuse/specular rgb, second colour rgb, eta or exponent} as in oracle/ref/ref_addon.cpp
+int ky_host_material_describe(int kind, const float* p, kyd_material* out)
+{
+    try
+    {
+        std::unique_ptr<material_t> m;
+        switch (kind)
+        {
+        case KYD_MAT_MATTE: m = std::make_unique<matte_material_t>(color_t(p[0], p[1], p[2])); break;
+        case KYD_MAT_MIRROR: m = std::make_unique<mirror_material_t>(color_t(p[0], p[1], p[2])); break;
+        case KYD_MAT_GLASS: m = std::make_unique<glass_material_t>(p[6], color_t(p[0], p[1], p[2]), color_t(p[3], p[4], p[5])); break;
+        case KYD_MAT_PLASTIC: m = std::make_unique<plastic_material_t>(color_t(p[0], p[1], p[2]), color_t(p[3], p[4], p[5]), p[6]); break;
+        default: throw std::runtime_error("unknown material kind");
+        }
+        *out = m->describe();
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+// the host-side LCG48 sampler: camera sample (2 floats) then n-2 get_float()
+void ky_host_sampler_floats(unsigned long long seed, int x, int y, int sample_index, int n, float* out)
+{
+    lcg48_sampler_t s(sample_index + 1, seed);
+    s.start_pixel();
+    for (int i = 0; i < sample_index; ++i) s.next_sample();
+    camera_sample_t cs = s.get_camera_sample({ (float)x, (float)y });
+    out[0] = cs.p_film.x - (float)x;
+    out[1] = cs.p_film.y - (float)y;
+    for (int i = 2; i < n; ++i) out[i] = s.get_float();
+}
+
 // runs one of the reference's entry points (ky.cpp:4675-4935) and copies the resulting film out.
 // name: "render_single_scene", "render_debug", "render_multiple_integrator", "render_direct_sample_enum",
 //       "render_multiple_scene", "render_mis_scene", "render_lighting_enum"

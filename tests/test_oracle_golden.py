@@ -1,0 +1,107 @@
+"""CPU: the C oracle (oracle/kyo.c) against the golden fixtures generated from the REFERENCE build
+(tests/golden/make_golden.py).  Bit-exact bar.  Runs wherever the repo is, /root/reference not needed."""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import ky_b200 as ky
+import kyo
+from golden.make_golden import MATERIAL_PARAMS, SHAPE_PARAMS
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILMS = np.load(os.path.join(HERE, "golden", "golden_films.npz"))
+KAT = np.load(os.path.join(HERE, "golden", "golden_kat.npz"))
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    b = np.ascontiguousarray(b, np.float32).view(np.uint32)
+    return a.shape == b.shape and np.array_equal(a, b)
+
+
+def nan_safe_mismatch(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    b = np.ascontiguousarray(b, np.float32).view(np.uint32)
+    return int((a != b).sum())
+
+
+@pytest.mark.parametrize("case", cases.film_cases(), ids=lambda c: c[0])
+def test_oracle_film_matches_reference_golden(case):
+    name, sk, integ, ds, depth, spp = case
+    scene = cases.make_scene(sk)
+    desc = ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds)
+    film, rays = kyo.render(scene, desc)
+    assert same_bits(film, FILMS[name]), f"{name}: {nan_safe_mismatch(film, FILMS[name])} floats differ"
+    assert rays == int(FILMS[name + "#rays"][0])
+
+
+def test_reference_mt19937_anchor():
+    # rng_t(1234) first draws, from the verbatim reference build
+    got = KAT["sampler/mt19937_seed1234"].view(np.uint32)[:4]
+    assert [hex(v) for v in got] == ["0x3f727dc5", "0x3d55e82d", "0x3f796cec", "0x3f721c91"]
+
+
+@pytest.mark.parametrize("key", [k for k in KAT.files if k.startswith("sampler/lcg48/")])
+def test_lcg48_stream(key):
+    want = KAT[key]
+    if key.endswith("seed99"):
+        seed, x, y, s = 99, 10, 20, 30
+    else:
+        seed = 1234
+        x, y, s = (int(v) for v in key.split("/")[-1].split("_"))
+    got = kyo.sampler_floats(ky.SAMPLER_LCG48, seed, x, y, s, len(want))
+    # the fixture's first two floats went through get_camera_sample: (pixel + u) - pixel (ky.cpp:971-974)
+    got[0] = (np.float32(x) + got[0]) - np.float32(x)
+    got[1] = (np.float32(y) + got[1]) - np.float32(y)
+    assert same_bits(got, want)
+    # the host class surface's sampler is the same stream
+    assert same_bits(ky.host_sampler_floats(seed, x, y, s, len(want)), want)
+    assert (want >= 0).all() and (want < 1).all()
+
+
+def test_erand48_family_anchor():
+    # the LCG is erand48's: X' = 0x5DEECE66D X + 0xB mod 2^48 (smallpt2pbrt/erand48.h); SURVEY.md A.2 KAT
+    x = 1 << 32  # seed {0,0,1}
+    x = (x * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+    assert x == 0xE66D0000000B
+    assert abs(x / 2.0 ** 48 - 0.90010070800785158) < 1e-17
+
+
+@pytest.mark.parametrize("name", list(SHAPE_PARAMS))
+def test_shape_functions(name):
+    kind, params = SHAPE_PARAMS[name]
+    shape = ky.describe_shape(kind, params)
+    assert same_bits(np.array([shape.area], np.float32), KAT[f"shape/{name}/area"])
+    got = kyo.shape_intersect(shape, KAT["shape/rays"])
+    want = KAT[f"shape/{name}/intersect"]
+    hit = want[:, 0] == 1
+    assert same_bits(got[:, 0], want[:, 0])
+    assert same_bits(got[hit], want[hit])
+    assert hit.sum() > 50
+    assert same_bits(kyo.shape_sample_direction(shape, KAT["shape/sample_in"]), KAT[f"shape/{name}/sample_direction"])
+    assert same_bits(kyo.shape_pdf_direction(shape, KAT["shape/pdf_in"]), KAT[f"shape/{name}/pdf_direction"])
+
+
+@pytest.mark.parametrize("name", list(MATERIAL_PARAMS))
+def test_bsdf_functions(name):
+    kind, params = MATERIAL_PARAMS[name]
+    material = ky.describe_material(kind, params)
+    got = kyo.material_bsdf(material, KAT["bsdf/in"])
+    want = KAT[f"bsdf/{name}"]
+    assert nan_safe_mismatch(got, want) == 0
+
+
+@pytest.mark.parametrize("sk", list(cases.SCENES))
+def test_camera_rays(sk):
+    scene = cases.make_scene(sk)
+    assert same_bits(kyo.camera_rays(scene, KAT["camera/in"]), KAT[f"camera/{sk}"])
+
+
+@pytest.mark.parametrize("key", [k for k in KAT.files if k.startswith("light/") and k != "light/in"])
+def test_light_sampling(key):
+    _, sk, idx = key.split("/")
+    scene = cases.make_scene(sk)
+    got = kyo.light_sample(scene, int(idx), KAT["light/in"])
+    assert nan_safe_mismatch(got, KAT[key]) == 0
