@@ -12,6 +12,7 @@ using namespace kyd;
 struct kyd_ctx
 {
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     std::string error;
@@ -156,8 +157,23 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
     if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_begin, stream));
 
     uint64_t launches = 0;
-    launch_render_pixels(rp, film_dev, ctx->counters_dev, stream);
-    launches += 1;
+    const bool wavefront = !(d->flags & KYD_FLAG_FUSED) &&
+        (d->integrator == KYD_INT_PT_ITERATION || d->integrator == KYD_INT_DIRECT_LIGHTING);
+    if (wavefront)
+    {
+        // wave size: the caller's choice, else 1 Mi paths (or the whole job if it is smaller)
+        const int64_t job = (int64_t)d->width * d->height * (int64_t)(d->sample_end - d->sample_begin);
+        int64_t capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 20;
+        if (capacity > job) capacity = job;
+        if (capacity < 1024) capacity = 1024;
+        KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, ctx->scene.n_lights));
+        launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches);
+    }
+    else
+    {
+        launch_render_pixels(rp, film_dev, ctx->counters_dev, stream);
+        launches += 1;
+    }
     KYD_CUDA(ctx, cudaGetLastError());
 
     if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_end, stream));
@@ -201,6 +217,7 @@ int kyd_create(kyd_ctx** out_ctx, int device)
     ctx->device = device;
     auto cleanup = [&](const std::string& msg) { g_create_error = msg; kyd_destroy(ctx); return KYD_ERR_CUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&ctx->ev_begin)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return cleanup(cudaGetErrorString(e));

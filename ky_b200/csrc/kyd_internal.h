@@ -24,8 +24,7 @@ struct WaveBuffers
     // path state, one entry per path slot
     float4* ray_o = nullptr;      // origin.xyz, tmax
     float4* ray_d = nullptr;      // direction.xyz, -
-    float4* hit = nullptr;        // hit normal.xyz, distance
-    int* hit_surface = nullptr;   // surface index or -1
+    float2* hit = nullptr;        // distance, surface index (int bits; -1 = miss)
     float4* beta = nullptr;       // throughput.rgb, flags (bit 0 previous vertex specular, bits 8.. bounce)
     float4* radiance = nullptr;   // Lo.rgb, -
     uint2* rng = nullptr;         // 48-bit LCG state
@@ -38,7 +37,7 @@ struct WaveBuffers
     uint2* vx_rng = nullptr;       // sampler state before the vertex' light loop
     // NEE queries: two per (vertex, light)
     float4* nee_o = nullptr;       // origin.xyz, tmax
-    float4* nee_d = nullptr;       // direction.xyz, light index (bits) | kind
+    float4* nee_d = nullptr;       // direction.xyz, bit 0: the reference issues this query
     float4* nee_value = nullptr;   // contribution if the query succeeds
     float4* nee_result = nullptr;  // per (light, slot): Ld of that light
     // queues of path slots
@@ -56,5 +55,11 @@ void launch_render_pixels(const RenderParams& rp, float* film_dev, DevCounters* 
 void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 
 void free_wave_buffers(WaveBuffers& w);
+// (re)allocates the wavefront buffers for `capacity` path slots and `lights` lights; returns a cudaError_t
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights);
+
+// wavefront path: path_tracing_iteration_t and direct_lighting_t.  Adds to `launches` the kernels it launched.
+void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
+                             cudaStream_t stream, int sm_count, uint64_t* launches);
 
 } // namespace kyd

@@ -4,6 +4,7 @@
 // Compile with -fmad=false (see kyd_device.cuh).
 #include "kyd_internal.h"
 #include "kyd_device.cuh"
+#include "kyd_wavefront.cuh"
 
 namespace kyd {
 
@@ -309,7 +310,9 @@ __global__ void __launch_bounds__(128) k_render_pixels(RenderParams rp, float* _
     if (idx < npix)
     {
         const int x = idx % rp.width, y = idx / rp.width;
-        float3 L = KYD_BLACK;
+        float* o = film + 3 * (size_t)idx;
+        // continuing a job (KYD_FLAG_ACCUMULATE) continues the pixel's running FP32 sum in sample order
+        float3 L = (rp.flags & KYD_FLAG_ACCUMULATE) ? V3(o[0], o[1], o[2]) : KYD_BLACK;
         for (int s = rp.sample_begin; s < rp.sample_end; ++s)
         {
             Sampler smp;
@@ -334,9 +337,6 @@ __global__ void __launch_bounds__(128) k_render_pixels(RenderParams rp, float* _
             }
             L = add(L, mul(Li, rp.weight)); // L = L + Li * (1. / spp), ky.cpp:3717-3721
         }
-        float* o = film + 3 * (size_t)idx;
-        if (rp.flags & KYD_FLAG_ACCUMULATE)
-            L = add(V3(o[0], o[1], o[2]), L);
         if (rp.flags & KYD_FLAG_CLAMP)
             L = V3(clamp_std(L.x, 0.f, 1.f), clamp_std(L.y, 0.f, 1.f), clamp_std(L.z, 0.f, 1.f));
         o[0] = L.x; o[1] = L.y; o[2] = L.z;
@@ -387,6 +387,122 @@ void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream)
     k_clamp<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(film_dev, n);
 }
 
-void free_wave_buffers(WaveBuffers&) {}
+// ---- wavefront orchestration ---------------------------------------------------------------------------
+template <class T>
+static cudaError_t alloc_array(T** p, size_t count)
+{
+    return cudaMalloc((void**)p, count * sizeof(T));
+}
+
+void free_wave_buffers(WaveBuffers& w)
+{
+    void* ptrs[] = { w.ray_o, w.ray_d, w.hit, w.beta, w.radiance, w.rng, w.vx_position, w.vx_normal, w.vx_wo, w.vx_color, w.vx_beta,
+                     w.vx_rng, w.nee_o, w.nee_d, w.nee_value, w.nee_result, w.queue_a, w.queue_b, w.queue_nee };
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    w = WaveBuffers{};
+}
+
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
+{
+    if (lights < 1) lights = 1;
+    if (w.capacity >= capacity && w.max_lights >= lights)
+        return cudaSuccess;
+    if (capacity < w.capacity) capacity = w.capacity;
+    if (lights < w.max_lights) lights = w.max_lights;
+    free_wave_buffers(w);
+    const size_t P = (size_t)capacity, L = (size_t)lights;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    ok(alloc_array(&w.ray_o, P)); ok(alloc_array(&w.ray_d, P)); ok(alloc_array(&w.hit, P));
+    ok(alloc_array(&w.beta, P)); ok(alloc_array(&w.radiance, P)); ok(alloc_array(&w.rng, P));
+    ok(alloc_array(&w.vx_position, P)); ok(alloc_array(&w.vx_normal, P)); ok(alloc_array(&w.vx_wo, P));
+    ok(alloc_array(&w.vx_color, P)); ok(alloc_array(&w.vx_beta, P)); ok(alloc_array(&w.vx_rng, P));
+    ok(alloc_array(&w.nee_o, 2 * L * P)); ok(alloc_array(&w.nee_d, 2 * L * P)); ok(alloc_array(&w.nee_value, 2 * L * P));
+    ok(alloc_array(&w.nee_result, L * P));
+    ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P)); ok(alloc_array(&w.queue_nee, P));
+    if (e != cudaSuccess)
+    {
+        free_wave_buffers(w);
+        return e;
+    }
+    w.capacity = capacity;
+    w.max_lights = lights;
+    return cudaSuccess;
+}
+
+void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
+                             cudaStream_t stream, int sm_count, uint64_t* launches)
+{
+    const long long npix_total = (long long)rp.width * rp.height;
+    const int nsamples = rp.sample_end - rp.sample_begin;
+    const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
+    const bool nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0;
+    const int last_bounce = direct_only ? 0 : rp.max_depth;
+
+    // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
+    const int grid256 = sm_count * 16, grid128 = sm_count * 24;
+
+    if (!(rp.flags & KYD_FLAG_ACCUMULATE))
+    {
+        k_zero<<<sm_count * 8, 256, 0, stream>>>(film_dev, npix_total * 3);
+        ++*launches;
+    }
+
+    // tile the film so that a wave fits the buffers; several samples per wave when the film is small
+    const long long cap = wave_paths < w.capacity ? wave_paths : w.capacity;
+    const long long tile = npix_total < cap ? npix_total : cap;
+    const int spp_per_wave = (int)((cap / tile) < 1 ? 1 : (cap / tile));
+
+    for (long long p0 = 0; p0 < npix_total; p0 += tile)
+    {
+        const int npix = (int)((npix_total - p0) < tile ? (npix_total - p0) : tile);
+        for (int s0 = 0; s0 < nsamples; s0 += spp_per_wave)
+        {
+            WaveParams wp{};
+            wp.rp = rp;
+            wp.pixel_begin = (int)p0;
+            wp.npix = npix;
+            wp.sample_begin = rp.sample_begin + s0;
+            wp.nspp = (nsamples - s0) < spp_per_wave ? (nsamples - s0) : spp_per_wave;
+            wp.nslots = npix * wp.nspp;
+            wp.plane = w.capacity;
+            wp.direct_only = direct_only ? 1 : 0;
+
+            k_raygen<<<grid256, 256, 0, stream>>>(wp, w, counters);
+            ++*launches;
+            for (int bounce = 0; bounce <= last_bounce; ++bounce)
+            {
+                const int qsel = bounce & 1, qnext = qsel ^ 1;
+                int* cur = qsel ? w.queue_b : w.queue_a;
+                int* next = qsel ? w.queue_a : w.queue_b;
+                if (bounce == 0)
+                {
+                    k_intersect<true><<<grid256, 256, 0, stream>>>(w, cur, counters, qsel, qnext);
+                    k_shade<true><<<grid128, 128, 0, stream>>>(wp, w, cur, next, w.queue_nee, counters, qsel, qnext, bounce);
+                }
+                else
+                {
+                    k_intersect<false><<<grid256, 256, 0, stream>>>(w, cur, counters, qsel, qnext);
+                    k_shade<false><<<grid128, 128, 0, stream>>>(wp, w, cur, next, w.queue_nee, counters, qsel, qnext, bounce);
+                }
+                *launches += 2;
+                if (nee)
+                {
+                    k_light_sample<<<grid128, 128, 0, stream>>>(wp, w, w.queue_nee, counters);
+                    k_shadow<<<grid256, 256, 0, stream>>>(wp, w, w.queue_nee, counters);
+                    *launches += 2;
+                }
+            }
+            k_accumulate<<<grid256, 256, 0, stream>>>(wp, w, film_dev);
+            ++*launches;
+        }
+    }
+    if (rp.flags & KYD_FLAG_CLAMP)
+    {
+        launch_clamp(film_dev, npix_total * 3, stream);
+        ++*launches;
+    }
+}
 
 } // namespace kyd

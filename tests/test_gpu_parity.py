@@ -1,6 +1,8 @@
 """GPU parity tests: the sm_100a path (through the C ABI, host buffers) against the C oracle and the
 golden films.  Bar: bit-exact films (byte identical float32) -- the only admitted deviation is the
 documented ~1e-8-per-call double-libm rounding difference, none of which occurs in these cases."""
+import os
+
 import numpy as np
 import pytest
 
@@ -9,6 +11,9 @@ import ky_b200 as ky
 import kyo
 
 pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FILMS = np.load(os.path.join(HERE, "golden", "golden_films.npz"))
 
 
 def _bits(a):
@@ -20,16 +25,74 @@ def _assert_same(got, want, what):
     assert not diff.any(), f"{what}: {int(diff.sum())} of {diff.size} pixels differ, max abs {np.nanmax(np.abs(got - want))}"
 
 
+# kernel organisations: the split wavefront (default), the same with waves far smaller than the film
+# (several tiles, or several samples per wave), and the per-pixel kernel
+MODES = {"wavefront": (0, 0), "wavefront_small_waves": (0, 1000), "wavefront_multi_spp": (0, cases.W * cases.H * 3), "pixel": (ky.FLAG_FUSED, 0)}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("case", cases.film_cases(), ids=lambda c: c[0])
-def test_film_matches_oracle(device, case):
+def test_film_matches_oracle_and_reference_golden(device, case, mode):
     name, sk, integ, ds, depth, spp = case
+    flags, wave = MODES[mode]
+    if mode != "wavefront" and integ not in (ky.INT_PT_ITERATION, ky.INT_DIRECT_LIGHTING):
+        pytest.skip("only one kernel organisation exists for this integrator")
     scene = cases.make_scene(sk)
-    desc = ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds)
+    desc = ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds, flags=ky.FLAG_CLAMP | flags)
+    device.set_wave_paths(wave)
     device.upload(scene)
     got = device.render(desc)
+    device.set_wave_paths(0)
     want, rays = kyo.render(scene, desc)
-    _assert_same(got, want, name)
+    _assert_same(got, want, name + " vs oracle")
+    _assert_same(got, FILMS[name], name + " vs reference golden")
     st = device.stats()
     assert st.samples == cases.W * cases.H * max(1, spp)
-    assert st.rays == rays, f"{name}: reference-equivalent ray count {st.rays} != oracle {rays}"
+    assert st.rays == rays == int(FILMS[name + "#rays"][0]), f"{name}: reference-equivalent ray count {st.rays} != oracle {rays}"
     assert st.rays_traced <= st.rays
+    assert st.kernel_launches >= 1
+
+
+@pytest.mark.parametrize("flags", [0, ky.FLAG_FUSED], ids=["wavefront", "pixel"])
+def test_sample_ranges_and_device_film_accumulation(device, flags):
+    """A job cut into sample ranges (what a multi-GPU split hands out) accumulated into one device-side film
+    equals the one-shot render bit for bit when the ranges are rendered in order."""
+    import torch
+    w, h, spp = 64, 40, 6
+    scene = ky.Scene(ky.SCENE_CORNELL, w, h)
+    device.upload(scene)
+    whole = device.render(ky.render_desc(w, h, spp, flags=ky.FLAG_CLAMP | flags))
+    film = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda")
+    for b, e in [(0, 1), (1, 4), (4, 6)]:
+        d = ky.render_desc(w, h, spp, sample_begin=b, sample_end=e, flags=ky.FLAG_ACCUMULATE | flags)
+        device.render_device(d, film.data_ptr())
+    device.clamp_device(film.data_ptr(), film.numel())
+    torch.cuda.synchronize()
+    _assert_same(film.cpu().numpy(), whole, "range-split film")
+    want, _ = kyo.render(scene, ky.render_desc(w, h, spp))
+    _assert_same(whole, want, "one-shot film")
+
+
+def test_debug_sampler(device):
+    scene = cases.make_scene("cornell")
+    desc = ky.render_desc(cases.W, cases.H, 2, sampler=ky.SAMPLER_DEBUG)
+    device.upload(scene)
+    for flags in (0, ky.FLAG_FUSED):
+        desc.flags = ky.FLAG_CLAMP | flags
+        got = device.render(desc)
+        want, _ = kyo.render(scene, desc)
+        _assert_same(got, want, "debug_sampler_t")
+
+
+def test_errors_are_reported_not_swallowed(device):
+    scene = cases.make_scene("cornell")
+    device.upload(scene)
+    bad = ky.render_desc(8, 8, 1, integrator=5)
+    with pytest.raises(RuntimeError, match="unsupported integrator"):
+        device.render(bad)
+    with pytest.raises(RuntimeError, match="spp must be positive"):
+        device.render(ky.render_desc(8, 8, 0, sample_end=1))
+    fresh = ky.Device(0)
+    with pytest.raises(RuntimeError, match="before kyd_upload_scene"):
+        fresh.render(ky.render_desc(8, 8, 1))
+    fresh.close()
