@@ -132,9 +132,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--spp-per-step", type=int, default=32)
-    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "pixel"], help="kernel organisation (kyd flags)")
+    ap.add_argument("--mode", default="wavefront", choices=["wavefront", "wavefront-split", "pixel"], help="kernel organisation (kyd flags)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--wave-paths", type=int, default=0, help="paths per wavefront (0 = library default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -154,10 +155,11 @@ def main():
     dev = ky.Device(local)
     scene = ky.Scene(ky.SCENE_CORNELL, WIDTH, HEIGHT, ky.CB_DEFAULT)
     dev.upload(scene)
+    dev.set_wave_paths(args.wave_paths)
     S = args.spp_per_step
     share = JOB_SPP // world
     base = rank * share
-    mode_flags = 0 if args.mode == "wavefront" else ky.FLAG_FUSED
+    mode_flags = {"wavefront": 0, "wavefront-split": ky.FLAG_SPLIT_LIGHT_SAMPLE, "pixel": ky.FLAG_FUSED}[args.mode]
 
     film = torch.zeros((HEIGHT, WIDTH, 3), dtype=torch.float32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -256,7 +258,7 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C5 cornell default_scene {WIDTH}x{HEIGHT}, path_tracing_iteration depth {DEPTH} both_mis, job {JOB_SPP} spp; "
                                    f"step = {S} spp slice per GPU (sample-index split across GPUs, one NCCL film reduce + clamp at the end)",
-                       "mode": args.mode, "l2": "flushed between timed steps (256 MiB write); each step also renders new sample indices",
+                       "mode": args.mode, "wave_paths": args.wave_paths, "l2": "flushed between timed steps (256 MiB write); each step also renders new sample indices",
                        "parallelism": f"spp-split x{world}"},
             "mrays_per_s": rays_all / (total_ms * 1e-3) / 1e6,
             "mrays_traced_per_s": traced_all / (total_ms * 1e-3) / 1e6,

@@ -152,8 +152,10 @@ enum kyd_render_flags
 {
     KYD_FLAG_CLAMP = 1u,       /* film = clamp01(sum), what render() hands to add_color (ky.cpp:3726);
                                   without it the raw partial sum is returned (multi-GPU partials) */
-    KYD_FLAG_FUSED = 2u,       /* one fused kernel per bounce instead of the split wavefront stages */
-    KYD_FLAG_ACCUMULATE = 4u   /* device film: add to what the buffer holds instead of overwriting */
+    KYD_FLAG_FUSED = 2u,       /* one thread per pixel running the whole integrator instead of the wavefront stages */
+    KYD_FLAG_ACCUMULATE = 4u,  /* device film: add to what the buffer holds instead of overwriting */
+    KYD_FLAG_SPLIT_LIGHT_SAMPLE = 8u /* wavefront: light-sample (NEE + MIS set-up) as its own kernel over (vertex, light)
+                                  pairs instead of inside shade; same results, kept for measurement */
 };
 
 typedef struct kyd_render_desc

@@ -161,9 +161,11 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         (d->integrator == KYD_INT_PT_ITERATION || d->integrator == KYD_INT_DIRECT_LIGHTING);
     if (wavefront)
     {
-        // wave size: the caller's choice, else 1 Mi paths (or the whole job if it is smaller)
+        // wave size: the caller's choice, else 16 Mi paths (or the whole job if it is smaller).  Measured on
+        // B200 (profiles/r01_wave_sweep.txt): throughput grows with the wave up to the whole 4K film --
+        // launch gaps and wave tails cost more than L2 residency of the path state would win.
         const int64_t job = (int64_t)d->width * d->height * (int64_t)(d->sample_end - d->sample_begin);
-        int64_t capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 20;
+        int64_t capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 24;
         if (capacity > job) capacity = job;
         if (capacity < 1024) capacity = 1024;
         KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, ctx->scene.n_lights));

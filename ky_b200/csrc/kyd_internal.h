@@ -13,7 +13,7 @@ struct DevCounters
 {
     unsigned long long rays;        // scene queries the reference issues for the same samples
     unsigned long long rays_traced; // scene queries actually traversed on the device
-    unsigned long long queue[8];    // wavefront queue tails (reset per use)
+    unsigned long long queue[16];   // wavefront queue tails (layout: kyd_wavefront.cuh)
 };
 
 // wavefront buffers (device memory owned by the context), capacity = paths per wave
@@ -21,29 +21,15 @@ struct WaveBuffers
 {
     int64_t capacity = 0;
     int max_lights = 0;
-    // path state, one entry per path slot
-    float4* ray_o = nullptr;      // origin.xyz, tmax
-    float4* ray_d = nullptr;      // direction.xyz, -
-    float2* hit = nullptr;        // distance, surface index (int bits; -1 = miss)
-    float4* beta = nullptr;       // throughput.rgb, flags (bit 0 previous vertex specular, bits 8.. bounce)
-    float4* radiance = nullptr;   // Lo.rgb, -
-    uint2* rng = nullptr;         // 48-bit LCG state
-    // vertex record written by shade for the light-sample stage
-    float4* vx_position = nullptr; // position.xyz, lobe
-    float4* vx_normal = nullptr;   // isect normal.xyz, exponent
-    float4* vx_wo = nullptr;       // wo.xyz, eta_t
-    float4* vx_color = nullptr;    // lobe colour a.rgb, -
-    float4* vx_beta = nullptr;     // throughput at the vertex (for the deferred Lo += beta * Ld), pending flag
-    uint2* vx_rng = nullptr;       // sampler state before the vertex' light loop
-    // NEE queries: two per (vertex, light)
-    float4* nee_o = nullptr;       // origin.xyz, tmax
-    float4* nee_d = nullptr;       // direction.xyz, bit 0: the reference issues this query
-    float4* nee_value = nullptr;   // contribution if the query succeeds
-    float4* nee_result = nullptr;  // per (light, slot): Ld of that light
+    // layouts: kyd_wavefront.cuh
+    float4* path = nullptr;       // one 128-byte line (8 float4) per path slot
+    float4* vertex = nullptr;     // 6 float4 per path slot: vertex record of the split light-sample stage
+    float4* nee = nullptr;        // one 128-byte line per (light, path slot): the two NEE queries and their result
     // queues of path slots
-    int* queue_a = nullptr;
+    int* queue_a = nullptr;        // ray queues (ping-pong by bounce parity)
     int* queue_b = nullptr;
-    int* queue_nee = nullptr;
+    int* queue_lobe[4] = {};       // hit paths sorted by BSDF lobe: Lambert, mirror, glass, Phong (LOBE_* order)
+    int* queue_nee[2] = {};        // vertices that sample lights: Lambert, Phong
 };
 
 void upload_scene_constant(const DevScene& scene, cudaStream_t stream);

@@ -396,8 +396,8 @@ static cudaError_t alloc_array(T** p, size_t count)
 
 void free_wave_buffers(WaveBuffers& w)
 {
-    void* ptrs[] = { w.ray_o, w.ray_d, w.hit, w.beta, w.radiance, w.rng, w.vx_position, w.vx_normal, w.vx_wo, w.vx_color, w.vx_beta,
-                     w.vx_rng, w.nee_o, w.nee_d, w.nee_value, w.nee_result, w.queue_a, w.queue_b, w.queue_nee };
+    void* ptrs[] = { w.path, w.vertex, w.nee, w.queue_a, w.queue_b, w.queue_lobe[0], w.queue_lobe[1],
+                     w.queue_lobe[2], w.queue_lobe[3], w.queue_nee[0], w.queue_nee[1] };
     for (void* p : ptrs)
         if (p) cudaFree(p);
     w = WaveBuffers{};
@@ -414,13 +414,12 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
     const size_t P = (size_t)capacity, L = (size_t)lights;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    ok(alloc_array(&w.ray_o, P)); ok(alloc_array(&w.ray_d, P)); ok(alloc_array(&w.hit, P));
-    ok(alloc_array(&w.beta, P)); ok(alloc_array(&w.radiance, P)); ok(alloc_array(&w.rng, P));
-    ok(alloc_array(&w.vx_position, P)); ok(alloc_array(&w.vx_normal, P)); ok(alloc_array(&w.vx_wo, P));
-    ok(alloc_array(&w.vx_color, P)); ok(alloc_array(&w.vx_beta, P)); ok(alloc_array(&w.vx_rng, P));
-    ok(alloc_array(&w.nee_o, 2 * L * P)); ok(alloc_array(&w.nee_d, 2 * L * P)); ok(alloc_array(&w.nee_value, 2 * L * P));
-    ok(alloc_array(&w.nee_result, L * P));
-    ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P)); ok(alloc_array(&w.queue_nee, P));
+    ok(alloc_array(&w.path, 8 * P));
+    ok(alloc_array(&w.vertex, 6 * P));
+    ok(alloc_array(&w.nee, 8 * L * P));
+    ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P));
+    for (int c = 0; c < 4; ++c) ok(alloc_array(&w.queue_lobe[c], P));
+    for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_nee[c], P));
     if (e != cudaSuccess)
     {
         free_wave_buffers(w);
@@ -468,30 +467,27 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.nslots = npix * wp.nspp;
             wp.plane = w.capacity;
             wp.direct_only = direct_only ? 1 : 0;
+            wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
 
             k_raygen<<<grid256, 256, 0, stream>>>(wp, w, counters);
             ++*launches;
             for (int bounce = 0; bounce <= last_bounce; ++bounce)
             {
-                const int qsel = bounce & 1, qnext = qsel ^ 1;
-                int* cur = qsel ? w.queue_b : w.queue_a;
-                int* next = qsel ? w.queue_a : w.queue_b;
                 if (bounce == 0)
-                {
-                    k_intersect<true><<<grid256, 256, 0, stream>>>(w, cur, counters, qsel, qnext);
-                    k_shade<true><<<grid128, 128, 0, stream>>>(wp, w, cur, next, w.queue_nee, counters, qsel, qnext, bounce);
-                }
+                    k_intersect<true><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
                 else
-                {
-                    k_intersect<false><<<grid256, 256, 0, stream>>>(w, cur, counters, qsel, qnext);
-                    k_shade<false><<<grid128, 128, 0, stream>>>(wp, w, cur, next, w.queue_nee, counters, qsel, qnext, bounce);
-                }
+                    k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
+                k_shade<<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
                 *launches += 2;
                 if (nee)
                 {
-                    k_light_sample<<<grid128, 128, 0, stream>>>(wp, w, w.queue_nee, counters);
-                    k_shadow<<<grid256, 256, 0, stream>>>(wp, w, w.queue_nee, counters);
-                    *launches += 2;
+                    if (wp.split_light_sample)
+                    {
+                        k_light_sample<<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        ++*launches;
+                    }
+                    k_shadow<<<grid256, 256, 0, stream>>>(wp, w, counters);
+                    ++*launches;
                 }
             }
             k_accumulate<<<grid256, 256, 0, stream>>>(wp, w, film_dev);

@@ -1,15 +1,32 @@
 // kyd_wavefront.cuh -- the wavefront organisation of path_tracing_iteration_t / direct_lighting_t
-// (reference ky.cpp:4523-4618, 4125-4155): separate raygen, intersect, shade (BSDF sample), light-sample
-// (NEE + MIS set-up), shadow (NEE ray queries) and accumulate kernels over SoA path state in HBM, with
-// warp-ballot compacted queues of path slots between them.  Included by kyd_kernels.cu only.
+// (reference ky.cpp:4523-4618, 4125-4155): raygen, intersect, shade (BSDF sample), light-sample (NEE + MIS
+// set-up), shadow (NEE ray queries) and accumulate kernels over path state in HBM, with warp-ballot
+// compacted queues of path slots between them.  Included by kyd_kernels.cu only.
 //
 // A wave is a tile of `npix` consecutive pixels times `nspp` consecutive sample indices; path slot
 // = s_local * npix + pixel_local.  Per-slot results do not depend on how the film is cut into waves.
 //
+// Divergence control (profiles/r01_wave1M_*: the first version ran shade at 11 of 32 lanes): the intersect
+// stage sorts the paths it hit by the BSDF lobe they will be shaded with (Lambert / Phong / mirror / glass;
+// a plastic surface picks its lobe with a hash of the hit, so the lobe is known there) into one queue per
+// lobe.  Shade and light-sample walk the queues one lobe after the other with lobe-specialised code, so a
+// warp never mixes lobes.  Paths that miss the scene are finished inside intersect.
+//
+// Data layout (profiles/r01_wave_lobe_soa_*: lobe-sorted queues turn the state accesses into gathers, and
+// 16-byte SoA elements then waste half of every 32-byte DRAM sector): the state of a path is ONE 128-byte
+// line, fields grouped by the sector the stages touch together:
+//     sector 0   ray origin.xyz, tmax | ray direction.xyz, flags          intersect reads, shade rewrites
+//     sector 1   beta.rgb, - | Lo.rgb, -                                   shade
+//     sector 2   beta of the vertex that sampled lights .rgb, pending | rng state, -     shade, accumulate
+//     sector 3   hit distance, surface, -, - | -                          intersect writes, shade reads
+// and the light-sampling record of a (light, path) pair is one line: the BSDF-sampled query (origin, tmax |
+// direction, flag | value), the light-sampled query (same three), and the estimator's result.
+// Every stage reads and writes whole sectors.
+//
 // Order of FP32 additions into a path's radiance Lo is the reference's: emitted light of a vertex, then
 // beta * Ld of that vertex (ky.cpp:4553-4576).  The Ld of a vertex becomes known one stage later than the
-// vertex is shaded, so it is added ("pending") at the start of the path's next shade, or by the accumulate
-// kernel if the path ended -- before anything else is added in both cases.
+// vertex is shaded, so it is added ("pending") at the start of the path's next shade (or when the path
+// misses, or by the accumulate kernel if the path ended) -- before anything else is added in every case.
 #pragma once
 
 #include "kyd_device.cuh"
@@ -17,8 +34,14 @@
 
 namespace kyd {
 
-enum { Q_CUR = 0, Q_NEXT = 1, Q_NEE = 2 };
+// queue tails in DevCounters::queue
+enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong) */, Q_LOBE0 = 4 /* + 4 * parity + lobe */ };
 enum { FLAG_PREV_SPECULAR = 1 };
+
+// float4 units of a path line / a light-sampling line
+enum { P_ORIGIN = 0, P_DIRECTION = 1, P_BETA = 2, P_RADIANCE = 3, P_VERTEX_BETA = 4, P_RNG = 5, P_HIT = 6, P_HIT_PAD = 7, PATH_UNITS = 8 };
+enum { N_BSDF_O = 0, N_BSDF_D = 1, N_BSDF_VALUE = 2, N_LIGHT_O = 3, N_LIGHT_D = 4, N_LIGHT_VALUE = 5, N_RESULT = 6, N_RESULT_PAD = 7, NEE_UNITS = 8 };
+enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_PAD = 5, VERTEX_UNITS = 6 };
 
 struct WaveParams
 {
@@ -26,12 +49,18 @@ struct WaveParams
     int pixel_begin, npix;    // tile of the film (linear pixel indices)
     int sample_begin, nspp;   // sample indices of this wave
     int nslots;               // npix * nspp
-    long long plane;          // stride between per-light planes of the NEE buffers (= capacity)
+    long long plane;          // lines between the per-light planes of the light-sampling buffer (= capacity)
     int direct_only;          // direct_lighting_t: stop after the first vertex' light loop
+    int split_light_sample;   // light-sample as its own kernel (KYD_FLAG_SPLIT_LIGHT_SAMPLE) instead of inside shade
 };
+
+KYD_DEV float4* path_line(const WaveBuffers& w, int slot) { return w.path + (size_t)slot * PATH_UNITS; }
+KYD_DEV float4* nee_line(const WaveBuffers& w, long long plane, int light, int slot) { return w.nee + ((size_t)light * plane + slot) * NEE_UNITS; }
+KYD_DEV float4* vertex_line(const WaveBuffers& w, int slot) { return w.vertex + (size_t)slot * VERTEX_UNITS; }
 
 KYD_DEV void flush_counters(unsigned rays, unsigned traced, DevCounters* counters)
 {
+    __syncwarp();
     rays = __reduce_add_sync(0xffffffffu, rays);
     traced = __reduce_add_sync(0xffffffffu, traced);
     if ((threadIdx.x & 31) == 0 && (rays | traced))
@@ -41,14 +70,17 @@ KYD_DEV void flush_counters(unsigned rays, unsigned traced, DevCounters* counter
     }
 }
 
-// warp-aggregated push: one atomic per warp, ballot + popc prefix for the lane offsets
+// warp-aggregated push: one atomic per warp, ballot + popc prefix for the lane offsets.  Must be reached
+// by all 32 lanes; the __syncwarp() makes them arrive together (without it the lanes of a diverged warp
+// execute the ballot / shuffle group by group: 18 % of the first version's shade instructions).
 KYD_DEV void queue_push(bool pred, int value, int* __restrict__ queue, unsigned long long* __restrict__ tail)
 {
-    unsigned mask = __ballot_sync(0xffffffffu, pred);
+    __syncwarp();
+    const unsigned mask = __ballot_sync(0xffffffffu, pred);
     if (mask == 0)
         return;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(mask) - 1;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
     unsigned long long base = 0;
     if (lane == leader)
         base = atomicAdd(tail, (unsigned long long)__popc(mask));
@@ -57,8 +89,25 @@ KYD_DEV void queue_push(bool pred, int value, int* __restrict__ queue, unsigned 
         queue[base + __popc(mask & ((1u << lane) - 1))] = value;
 }
 
-KYD_DEV uint2 pack_rng(unsigned long long s) { return make_uint2((unsigned)s, (unsigned)(s >> 32)); }
-KYD_DEV unsigned long long unpack_rng(uint2 v) { return (unsigned long long)v.x | ((unsigned long long)v.y << 32); }
+KYD_DEV unsigned long long unpack_rng(float4 v) { return (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32); }
+KYD_DEV float4 pack_rng(unsigned long long s) { return make_float4(__uint_as_float((unsigned)s), __uint_as_float((unsigned)(s >> 32)), 0.f, 0.f); }
+
+// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576
+KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, float4 vb, float3 Lo)
+{
+    const int pending = __float_as_int(vb.w);
+    if (pending > 0)
+    {
+        float3 Ld = KYD_BLACK;
+        for (int l = 0; l < pending; ++l)
+        {
+            float4 e = nee_line(w, plane, l, slot)[N_RESULT];
+            Ld = add(Ld, V3(e.x, e.y, e.z));
+        }
+        Lo = add(Lo, cmulc(V3(vb.x, vb.y, vb.z), Ld));
+    }
+    return Lo;
+}
 
 // ---- raygen: camera_t::generate_ray for every slot of the wave (ky.cpp:3714-3715) ----------------------
 __global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
@@ -73,163 +122,91 @@ __global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, De
         smp.start(wp.rp.sampler, wp.rp.seed, x, y, s);
         float2 jitter = smp.get_float2();
         Ray r = generate_ray((float)x + jitter.x, (float)y + jitter.y);
-        w.ray_o[slot] = make_float4(r.o.x, r.o.y, r.o.z, r.tmax);
-        w.ray_d[slot] = make_float4(r.d.x, r.d.y, r.d.z, 0.f);
-        w.beta[slot] = make_float4(1.f, 1.f, 1.f, __int_as_float(0)); // w: flags | bounce << 8
-        w.radiance[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-        w.vx_beta[slot] = make_float4(0.f, 0.f, 0.f, 0.f);            // w: pending light count
-        w.rng[slot] = pack_rng(smp.state);
+        float4* p = path_line(w, slot);
+        p[P_ORIGIN] = make_float4(r.o.x, r.o.y, r.o.z, r.tmax);
+        p[P_DIRECTION] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(0));
+        p[P_BETA] = make_float4(1.f, 1.f, 1.f, 0.f);
+        p[P_RADIANCE] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p[P_VERTEX_BETA] = make_float4(0.f, 0.f, 0.f, __int_as_float(0)); // w: pending light count
+        p[P_RNG] = pack_rng(smp.state);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        counters->queue[Q_CUR] = (unsigned long long)wp.nslots;
-        counters->queue[Q_NEXT] = 0;
-        counters->queue[Q_NEE] = 0;
-    }
+    if (blockIdx.x == 0 && threadIdx.x < 16)
+        counters->queue[threadIdx.x] = threadIdx.x == Q_RAY0 ? (unsigned long long)wp.nslots : 0ull;
+}
+
+// the lobe material_t::scattering will build for this hit (ky.cpp:2587-2671); pure function of the hit
+KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
+{
+    const DevMaterial& m = c_scene.materials[c_scene.surf_material[surface]];
+    if (m.kind == KYD_MAT_MATTE) return LOBE_LAMBERT;
+    if (m.kind == KYD_MAT_MIRROR) return LOBE_MIRROR;
+    if (m.kind == KYD_MAT_GLASS) return LOBE_FRESNEL;
+    return plastic_random(ray_at(r, t), neg(r.d)) < m.p_specular ? LOBE_PHONG : LOBE_LAMBERT;
 }
 
 // ---- intersect: scene_t::intersect closest-hit query for every queued path (ky.cpp:3172-3184) -------------
-// identity == true: the queue is 0..n-1 (first bounce of a wave)
+// IDENTITY: the queue is 0..n-1 (first bounce of a wave).  Hits go to the queue of their lobe; a miss ends
+// the path here (ky.cpp:4555-4563).
 template <bool IDENTITY>
-__global__ void __launch_bounds__(256) k_intersect(WaveBuffers w, const int* __restrict__ queue, DevCounters* __restrict__ counters, int qsel, int qnext)
+__global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
-    const int n = (int)counters->queue[qsel];
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    const int parity = bounce & 1;
+    const int n = (int)counters->queue[Q_RAY0 + parity];
+    if (blockIdx.x == 0 && threadIdx.x < 7)
     {
-        // the tails this bounce's shade will push to (their previous contents were consumed by earlier kernels)
-        counters->queue[qnext] = 0;
-        counters->queue[Q_NEE] = 0;
+        // tails that later kernels of this bounce push to; their previous contents were consumed by earlier kernels
+        const int which[7] = { Q_RAY0 + (parity ^ 1), Q_NEE0, Q_NEE0 + 1, Q_LOBE0 + 4 * (parity ^ 1), Q_LOBE0 + 4 * (parity ^ 1) + 1,
+                               Q_LOBE0 + 4 * (parity ^ 1) + 2, Q_LOBE0 + 4 * (parity ^ 1) + 3 };
+        counters->queue[which[threadIdx.x]] = 0;
     }
+    const int* __restrict__ queue = parity ? w.queue_b : w.queue_a;
+    unsigned long long* tails = &counters->queue[Q_LOBE0 + 4 * parity];
+    const bool has_env = c_scene.env_light >= 0;
     const int stride = gridDim.x * blockDim.x;
     unsigned rays = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    {
-        const int slot = IDENTITY ? i : queue[i];
-        float4 o = w.ray_o[slot], d = w.ray_d[slot];
-        Ray r;
-        r.o = V3(o.x, o.y, o.z);
-        r.d = V3(d.x, d.y, d.z);
-        r.tmax = o.w;
-        float t;
-        int s = scene_closest(r, &t);
-        w.hit[slot] = make_float2(t, __int_as_float(s));
-        rays++;
-    }
-    flush_counters(rays, rays, counters);
-}
-
-// ---- shade: one path vertex (ky.cpp:4545-4613 without the light loop) ----------------------------------
-template <bool IDENTITY>
-__global__ void __launch_bounds__(128) k_shade(WaveParams wp, WaveBuffers w, const int* __restrict__ queue, int* __restrict__ next_queue,
-                                               int* __restrict__ nee_queue, DevCounters* __restrict__ counters, int qsel, int qnext, int bounce)
-{
-    const int n = (int)counters->queue[qsel];
-    const int stride = gridDim.x * blockDim.x;
-    const int n_lights = c_scene.n_lights;
     const int base_i = blockIdx.x * blockDim.x + threadIdx.x;
-    // whole warps iterate together so that the ballots in queue_push are convergent
     for (int i0 = base_i - (threadIdx.x & 31); i0 < n; i0 += stride)
     {
         const int i = i0 + (threadIdx.x & 31);
-        bool alive = false, wants_nee = false;
-        int slot = 0;
+        int lobe = -1, slot = 0;
         if (i < n)
         {
             slot = IDENTITY ? i : queue[i];
-            float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot], b4 = w.beta[slot], L4 = w.radiance[slot];
-            float2 h = w.hit[slot];
+            float4* p = path_line(w, slot);
+            float4 o = p[P_ORIGIN], d = p[P_DIRECTION];
             Ray r;
-            r.o = V3(o4.x, o4.y, o4.z);
-            r.d = V3(d4.x, d4.y, d4.z);
-            r.tmax = o4.w;
-            float3 beta = V3(b4.x, b4.y, b4.z), Lo = V3(L4.x, L4.y, L4.z);
-            const int flags = __float_as_int(b4.w);
-            const int surface = __float_as_int(h.y);
-            const bool hit = surface >= 0;
-
-            // light gathered at the previous vertex (see file header)
-            float4 vb = w.vx_beta[slot];
-            const int pending = __float_as_int(vb.w);
-            if (pending > 0)
+            r.o = V3(o.x, o.y, o.z);
+            r.d = V3(d.x, d.y, d.z);
+            r.tmax = o.w;
+            float t;
+            const int s = scene_closest(r, &t);
+            rays++;
+            if (s >= 0)
             {
-                float3 Ld = KYD_BLACK;
-                for (int l = 0; l < pending; ++l)
-                {
-                    float4 e = w.nee_result[(long long)l * wp.plane + slot];
-                    Ld = add(Ld, V3(e.x, e.y, e.z));
-                }
-                Lo = add(Lo, cmulc(V3(vb.x, vb.y, vb.z), Ld));
+                p[P_HIT] = make_float4(t, __int_as_float(s), 0.f, 0.f);
+                p[P_HIT_PAD] = make_float4(0.f, 0.f, 0.f, 0.f);
+                lobe = classify_lobe(s, r, t);
             }
-            int new_pending = 0;
-
-            HitGeom g;
-            if (hit)
-                g = shape_hit_geom(c_scene.surf_shape[surface], r, h.x);
-
-            if (bounce == 0 || (flags & FLAG_PREV_SPECULAR))
-                Lo = add(Lo, cmulc(beta, hit ? surface_emission(surface, g) : environment_lighting()));
-
-            if (hit && bounce < wp.rp.max_depth + wp.direct_only)
+            else if (has_env && (bounce == 0 || (__float_as_int(d.w) & FLAG_PREV_SPECULAR)))
             {
-                Bsdf b;
-                material_scattering(c_scene.materials[c_scene.surf_material[surface]], g, &b);
-                Sampler smp;
-                smp.debug = (wp.rp.sampler == KYD_SAMPLER_DEBUG);
-                smp.state = unpack_rng(w.rng[slot]);
-
-                if (!bsdf_is_delta(b.lobe))
+                // Lo += beta * environment_lighting at the camera vertex or after a specular bounce
+                float4 b4 = p[P_BETA], L4 = p[P_RADIANCE], vb = p[P_VERTEX_BETA];
+                float3 Lo = add_pending(w, wp.plane, slot, vb, V3(L4.x, L4.y, L4.z));
+                Lo = add(Lo, cmulc(V3(b4.x, b4.y, b4.z), environment_lighting()));
+                p[P_BETA] = b4;
+                p[P_RADIANCE] = make_float4(Lo.x, Lo.y, Lo.z, 0.f);
+                if (__float_as_int(vb.w) > 0)
                 {
-                    if (wp.rp.direct_sample != KYD_DS_IDLE && n_lights > 0)
-                    {
-                        // vertex record for the light-sample stage
-                        w.vx_position[slot] = make_float4(g.position.x, g.position.y, g.position.z, __int_as_float(b.lobe));
-                        w.vx_normal[slot] = make_float4(g.normal.x, g.normal.y, g.normal.z, b.exponent);
-                        w.vx_wo[slot] = make_float4(g.wo.x, g.wo.y, g.wo.z, 0.f);
-                        w.vx_color[slot] = make_float4(b.a.x, b.a.y, b.a.z, 0.f);
-                        w.vx_rng[slot] = pack_rng(smp.state);
-                        new_pending = n_lights;
-                        wants_nee = true;
-                    }
-                    // sample_all_light draws 4 floats per light, plus 2 per non-delta light in `bsdf` mode
-                    smp.skip(4 * n_lights + (wp.rp.direct_sample == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
-                }
-
-                if (!wp.direct_only)
-                {
-                    BsdfSample bs = bsdf_sample(b, g.wo, smp.get_float2());
-                    if (!(is_black(bs.f) || bs.pdf == 0.f))
-                    {
-                        float3 vertex_beta = beta;
-                        beta = cmulc(beta, cdiv(mul(bs.f, abs_dot(bs.wi, g.normal)), bs.pdf));
-                        Ray nr = spawn_ray(g, bs.wi);
-                        alive = true;
-                        if (bounce > 3)
-                        {
-                            float q = max_std(0.05f, 1 - max_component(beta));
-                            if (smp.get_float() < q)
-                                alive = false;
-                            else
-                                beta = mul(beta, 1 / (1 - q));
-                        }
-                        if (alive)
-                        {
-                            w.ray_o[slot] = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.tmax);
-                            w.ray_d[slot] = make_float4(nr.d.x, nr.d.y, nr.d.z, 0.f);
-                            w.beta[slot] = make_float4(beta.x, beta.y, beta.z, __int_as_float((bs.type & BSDF_SPECULAR) ? FLAG_PREV_SPECULAR : 0));
-                            w.rng[slot] = pack_rng(smp.state);
-                        }
-                        beta = vertex_beta;
-                    }
+                    p[P_VERTEX_BETA] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+                    p[P_RNG] = p[P_RNG];
                 }
             }
-            // beta of THIS vertex multiplies its Ld later
-            if (new_pending > 0 || pending > 0)
-                w.vx_beta[slot] = make_float4(beta.x, beta.y, beta.z, __int_as_float(new_pending));
-            w.radiance[slot] = make_float4(Lo.x, Lo.y, Lo.z, 0.f);
         }
-        queue_push(alive, slot, next_queue, &counters->queue[qnext]);
-        queue_push(wants_nee, slot, nee_queue, &counters->queue[Q_NEE]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            queue_push(lobe == c, slot, w.queue_lobe[c], &tails[c]);
     }
+    flush_counters(rays, rays, counters);
 }
 
 // draws consumed by sample_all_light before light l (ky.cpp:3864-3869, 3900)
@@ -242,27 +219,205 @@ KYD_DEV int light_draw_offset(int l, int direct_sample)
     return n;
 }
 
-KYD_DEV void store_nee(const WaveBuffers& w, long long at, const NeeRay& q)
+KYD_DEV void store_nee(float4* line, int first_unit, const NeeRay& q)
 {
-    // tmax < 0 marks "no query"; w of nee_d: bit 0 = the reference issues this query (ray statistics)
-    w.nee_o[at] = make_float4(q.ray.o.x, q.ray.o.y, q.ray.o.z, q.active ? q.ray.tmax : -1.f);
-    w.nee_d[at] = make_float4(q.ray.d.x, q.ray.d.y, q.ray.d.z, __int_as_float(q.ref_query ? 1 : 0));
-    w.nee_value[at] = make_float4(q.value.x, q.value.y, q.value.z, 0.f);
+    // tmax < 0 marks "no query"; w of the direction: bit 0 = the reference issues this query (ray statistics)
+    line[first_unit] = make_float4(q.ray.o.x, q.ray.o.y, q.ray.o.z, q.active ? q.ray.tmax : -1.f);
+    line[first_unit + 1] = make_float4(q.ray.d.x, q.ray.d.y, q.ray.d.z, __int_as_float(q.ref_query ? 1 : 0));
+    line[first_unit + 2] = make_float4(q.value.x, q.value.y, q.value.z, 0.f);
 }
 
-// ---- light-sample: NEE + MIS set-up for every (vertex, light) (ky.cpp:3864-3869 + first halves of 3889-4074)
-__global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers w, const int* __restrict__ nee_queue, DevCounters* __restrict__ counters)
+// NEE + MIS set-up of one (vertex, light): the two draws, the first halves of the estimators
+// (ky.cpp:3864-3869, 3889-4074), and the queries written to the pair's line
+KYD_DEV void light_sample_pair(const WaveParams& wp, const WaveBuffers& w, const HitGeom& g, const Bsdf& b, int l, int slot, Sampler smp)
 {
-    const int n = (int)counters->queue[Q_NEE];
+    const int ds = wp.rp.direct_sample;
+    float2 random_bsdf = smp.get_float2();
+    float2 random_light = smp.get_float2();
+
+    NeeRay qb, ql;
+    qb.active = ql.active = false;
+    qb.ref_query = ql.ref_query = false;
+    qb.value = ql.value = KYD_BLACK;
+    qb.ray.o = qb.ray.d = ql.ray.o = ql.ray.d = V3(0, 0, 0);
+    qb.ray.tmax = ql.ray.tmax = -1.f;
+    if (ds == KYD_DS_BSDF)
+    {
+        if (!light_is_delta(c_scene.lights[l].kind))
+            qb = nee_bsdf_setup(g, b, l, smp.get_float2(), false);
+    }
+    else if (ds == KYD_DS_BSDF_MIS || ds == KYD_DS_BOTH_MIS)
+        qb = nee_bsdf_setup(g, b, l, random_bsdf, true);
+    if (ds == KYD_DS_LIGHT)
+        ql = nee_light_setup(g, b, l, random_light, false);
+    else if (ds == KYD_DS_LIGHT_MIS || ds == KYD_DS_BOTH_MIS)
+        ql = nee_light_setup(g, b, l, random_light, true);
+
+    float4* line = nee_line(w, wp.plane, l, slot);
+    store_nee(line, N_BSDF_O, qb);
+    store_nee(line, N_LIGHT_O, ql);
+}
+
+// ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
+template <int LOBE>
+KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee)
+{
+    float4* p = path_line(w, slot);
+    float4 o4 = p[P_ORIGIN], d4 = p[P_DIRECTION], b4 = p[P_BETA], L4 = p[P_RADIANCE], vb = p[P_VERTEX_BETA], rng4 = p[P_RNG], h = p[P_HIT];
+    Ray r;
+    r.o = V3(o4.x, o4.y, o4.z);
+    r.d = V3(d4.x, d4.y, d4.z);
+    r.tmax = o4.w;
+    float3 beta = V3(b4.x, b4.y, b4.z);
+    const int flags = __float_as_int(d4.w);
+    const int surface = __float_as_int(h.y);
+
+    // light gathered at the previous vertex (see file header)
+    float3 Lo = add_pending(w, wp.plane, slot, vb, V3(L4.x, L4.y, L4.z));
+    int new_pending = 0;
+
+    HitGeom g = shape_hit_geom(c_scene.surf_shape[surface], r, h.x);
+
+    if (bounce == 0 || (flags & FLAG_PREV_SPECULAR))
+        Lo = add(Lo, cmulc(beta, surface_emission(surface, g)));
+
+    float3 next_beta = beta;
+    unsigned long long rng_state = unpack_rng(rng4);
+    if (bounce < wp.rp.max_depth + wp.direct_only)
+    {
+        const DevMaterial& m = c_scene.materials[c_scene.surf_material[surface]];
+        Bsdf b;
+        b.f = frame_from_z(g.normal);
+        b.t = KYD_BLACK;
+        b.eta_t = 1.f;
+        b.exponent = 0.f;
+        b.lobe = LOBE;
+        if (LOBE == LOBE_LAMBERT) b.a = m.kind == KYD_MAT_PLASTIC ? m.plastic_lambert : m.diffuse;
+        else if (LOBE == LOBE_PHONG) { b.a = m.plastic_phong; b.exponent = m.exponent; }
+        else if (LOBE == LOBE_MIRROR) b.a = m.specular;
+        else { b.a = m.specular; b.t = m.transmission; b.eta_t = m.eta; }
+
+        Sampler smp;
+        smp.debug = (wp.rp.sampler == KYD_SAMPLER_DEBUG);
+        smp.state = rng_state;
+
+        if (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG)
+        {
+            if (wp.rp.direct_sample != KYD_DS_IDLE && n_lights > 0)
+            {
+                if (wp.split_light_sample)
+                {
+                    // vertex record for the light-sample stage
+                    float4* v = vertex_line(w, slot);
+                    v[V_POSITION] = make_float4(g.position.x, g.position.y, g.position.z, 0.f);
+                    v[V_NORMAL] = make_float4(g.normal.x, g.normal.y, g.normal.z, b.exponent);
+                    v[V_WO] = make_float4(g.wo.x, g.wo.y, g.wo.z, 0.f);
+                    v[V_COLOR] = make_float4(b.a.x, b.a.y, b.a.z, 0.f);
+                    v[V_RNG] = pack_rng(smp.state);
+                    v[V_PAD] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                else
+                {
+                    Sampler ls = smp;
+                    for (int l = 0; l < n_lights; ++l)
+                    {
+                        light_sample_pair(wp, w, g, b, l, slot, ls);
+                        ls.skip(4 + ((wp.rp.direct_sample == KYD_DS_BSDF && !light_is_delta(c_scene.lights[l].kind)) ? 2 : 0));
+                    }
+                }
+                new_pending = n_lights;
+                *out_nee = true;
+            }
+            // sample_all_light draws 4 floats per light, plus 2 per non-delta light in `bsdf` mode
+            smp.skip(4 * n_lights + (wp.rp.direct_sample == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
+        }
+
+        if (!wp.direct_only)
+        {
+            BsdfSample bs = bsdf_sample(b, g.wo, smp.get_float2());
+            if (!(is_black(bs.f) || bs.pdf == 0.f))
+            {
+                float3 nb = cmulc(beta, cdiv(mul(bs.f, abs_dot(bs.wi, g.normal)), bs.pdf));
+                Ray nr = spawn_ray(g, bs.wi);
+                bool alive = true;
+                if (bounce > 3)
+                {
+                    float q = max_std(0.05f, 1 - max_component(nb));
+                    if (smp.get_float() < q)
+                        alive = false;
+                    else
+                        nb = mul(nb, 1 / (1 - q));
+                }
+                if (alive)
+                {
+                    o4 = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.tmax);
+                    d4 = make_float4(nr.d.x, nr.d.y, nr.d.z, __int_as_float((bs.type & BSDF_SPECULAR) ? FLAG_PREV_SPECULAR : 0));
+                    next_beta = nb;
+                    rng_state = smp.state;
+                    *out_alive = true;
+                }
+            }
+        }
+    }
+    // whole sectors go back: the ray, (beta, Lo), (beta of this vertex for its pending Ld, rng)
+    p[P_ORIGIN] = o4;
+    p[P_DIRECTION] = d4;
+    p[P_BETA] = make_float4(next_beta.x, next_beta.y, next_beta.z, 0.f);
+    p[P_RADIANCE] = make_float4(Lo.x, Lo.y, Lo.z, 0.f);
+    p[P_VERTEX_BETA] = make_float4(beta.x, beta.y, beta.z, __int_as_float(new_pending));
+    p[P_RNG] = pack_rng(rng_state);
+}
+
+template <int LOBE>
+KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
+{
+    const int parity = bounce & 1;
+    const int n = (int)counters->queue[Q_LOBE0 + 4 * parity + LOBE];
+    const int* __restrict__ queue = w.queue_lobe[LOBE];
+    int* __restrict__ next_queue = parity ? w.queue_a : w.queue_b;
+    const int stride = gridDim.x * blockDim.x;
+    const int n_lights = c_scene.n_lights;
+    const int base_i = blockIdx.x * blockDim.x + threadIdx.x;
+    // whole warps iterate together so that the ballots in queue_push are convergent
+    for (int i0 = base_i - (threadIdx.x & 31); i0 < n; i0 += stride)
+    {
+        const int i = i0 + (threadIdx.x & 31);
+        bool alive = false, wants_nee = false;
+        int slot = 0;
+        if (i < n)
+        {
+            slot = queue[i];
+            shade_vertex<LOBE>(wp, w, slot, bounce, n_lights, &alive, &wants_nee);
+        }
+        queue_push(alive, slot, next_queue, &counters->queue[Q_RAY0 + (parity ^ 1)]);
+        if (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG)
+            queue_push(wants_nee, slot, w.queue_nee[LOBE == LOBE_PHONG], &counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)]);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
+{
+    shade_queue<LOBE_LAMBERT>(wp, w, counters, bounce);
+    shade_queue<LOBE_PHONG>(wp, w, counters, bounce);
+    shade_queue<LOBE_MIRROR>(wp, w, counters, bounce);
+    shade_queue<LOBE_FRESNEL>(wp, w, counters, bounce);
+}
+
+// ---- light-sample as its own stage (KYD_FLAG_SPLIT_LIGHT_SAMPLE): one thread per (vertex, light) -------------
+template <int LOBE>
+KYD_DEV void light_sample_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters)
+{
+    const int n = (int)counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)];
+    const int* __restrict__ nee_queue = w.queue_nee[LOBE == LOBE_PHONG];
     const int n_lights = c_scene.n_lights;
     const long long total = (long long)n * n_lights;
     const int stride = gridDim.x * blockDim.x;
-    const int ds = wp.rp.direct_sample;
     for (long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
     {
         const int l = (int)(idx / n);            // light-major: a warp works on one light
         const int slot = nee_queue[idx - (long long)l * n];
-        float4 p4 = w.vx_position[slot], n4 = w.vx_normal[slot], wo4 = w.vx_wo[slot], c4 = w.vx_color[slot];
+        const float4* v = vertex_line(w, slot);
+        float4 p4 = v[V_POSITION], n4 = v[V_NORMAL], wo4 = v[V_WO], c4 = v[V_COLOR], rng4 = v[V_RNG];
         HitGeom g;
         g.position = V3(p4.x, p4.y, p4.z);
         g.normal = V3(n4.x, n4.y, n4.z);
@@ -273,97 +428,83 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
         b.t = KYD_BLACK;
         b.eta_t = 1.f;
         b.exponent = n4.w;
-        b.lobe = __float_as_int(p4.w);
+        b.lobe = LOBE;
 
         Sampler smp;
         smp.debug = (wp.rp.sampler == KYD_SAMPLER_DEBUG);
-        smp.state = unpack_rng(w.vx_rng[slot]);
-        smp.skip(light_draw_offset(l, ds));
-        float2 random_bsdf = smp.get_float2();
-        float2 random_light = smp.get_float2();
-
-        NeeRay qb, ql;
-        qb.active = ql.active = false;
-        qb.ref_query = ql.ref_query = false;
-        qb.value = ql.value = KYD_BLACK;
-        qb.ray.o = qb.ray.d = ql.ray.o = ql.ray.d = V3(0, 0, 0);
-        qb.ray.tmax = ql.ray.tmax = -1.f;
-        if (ds == KYD_DS_BSDF)
-        {
-            if (!light_is_delta(c_scene.lights[l].kind))
-                qb = nee_bsdf_setup(g, b, l, smp.get_float2(), false);
-        }
-        else if (ds == KYD_DS_BSDF_MIS || ds == KYD_DS_BOTH_MIS)
-            qb = nee_bsdf_setup(g, b, l, random_bsdf, true);
-        if (ds == KYD_DS_LIGHT)
-            ql = nee_light_setup(g, b, l, random_light, false);
-        else if (ds == KYD_DS_LIGHT_MIS || ds == KYD_DS_BOTH_MIS)
-            ql = nee_light_setup(g, b, l, random_light, true);
-
-        const long long at = (long long)(2 * l) * wp.plane + slot;
-        store_nee(w, at, qb);
-        store_nee(w, at + wp.plane, ql);
+        smp.state = unpack_rng(rng4);
+        smp.skip(light_draw_offset(l, wp.rp.direct_sample));
+        light_sample_pair(wp, w, g, b, l, slot, smp);
     }
+}
+
+__global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
+{
+    light_sample_queue<LOBE_LAMBERT>(wp, w, counters);
+    light_sample_queue<LOBE_PHONG>(wp, w, counters);
 }
 
 // ---- shadow: the scene queries of the light loop and the estimators' second halves ------------------------
 // closest-hit query for the BSDF-sampled direction, occlusion query for the light-sampled point; writes
 // the estimator value of (vertex, light): Lb, Ll or 0.5 Lb + 0.5 Ll (ky.cpp:4083)
-__global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, const int* __restrict__ nee_queue, DevCounters* __restrict__ counters)
+__global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
 {
-    const int n = (int)counters->queue[Q_NEE];
     const int n_lights = c_scene.n_lights;
-    const long long total = (long long)n * n_lights;
     const int stride = gridDim.x * blockDim.x;
     const int ds = wp.rp.direct_sample;
     unsigned rays = 0, traced = 0;
-    for (long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+    for (int c = 0; c < 2; ++c)
     {
-        const int l = (int)(idx / n);
-        const int slot = nee_queue[idx - (long long)l * n];
-        const long long at = (long long)(2 * l) * wp.plane + slot;
+        const int n = (int)counters->queue[Q_NEE0 + c];
+        const int* __restrict__ nee_queue = w.queue_nee[c];
+        const long long total = (long long)n * n_lights;
+        for (long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+        {
+            const int l = (int)(idx / n);
+            const int slot = nee_queue[idx - (long long)l * n];
+            float4* line = nee_line(w, wp.plane, l, slot);
 
-        float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
-        {
-            float4 o = w.nee_o[at], d = w.nee_d[at];
-            rays += (unsigned)(__float_as_int(d.w) & 1);
-            if (o.w >= 0.f)
+            float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
             {
-                NeeRay q;
-                q.ray.o = V3(o.x, o.y, o.z);
-                q.ray.d = V3(d.x, d.y, d.z);
-                q.ray.tmax = o.w;
-                float4 v = w.nee_value[at];
-                q.value = V3(v.x, v.y, v.z);
-                q.light = l;
-                float t;
-                int s = scene_closest(q.ray, &t);
-                Lb = nee_bsdf_resolve(q, s, t);
-                traced++;
+                float4 o = line[N_BSDF_O], d = line[N_BSDF_D], v = line[N_BSDF_VALUE];
+                rays += (unsigned)(__float_as_int(d.w) & 1);
+                if (o.w >= 0.f)
+                {
+                    NeeRay q;
+                    q.ray.o = V3(o.x, o.y, o.z);
+                    q.ray.d = V3(d.x, d.y, d.z);
+                    q.ray.tmax = o.w;
+                    q.value = V3(v.x, v.y, v.z);
+                    q.light = l;
+                    float t;
+                    int s = scene_closest(q.ray, &t);
+                    Lb = nee_bsdf_resolve(q, s, t);
+                    traced++;
+                }
             }
-        }
-        {
-            float4 o = w.nee_o[at + wp.plane], d = w.nee_d[at + wp.plane];
-            rays += (unsigned)(__float_as_int(d.w) & 1);
-            if (o.w >= 0.f)
             {
-                Ray r;
-                r.o = V3(o.x, o.y, o.z);
-                r.d = V3(d.x, d.y, d.z);
-                r.tmax = o.w;
-                float4 v = w.nee_value[at + wp.plane];
-                Ll = scene_any_hit(r) ? KYD_BLACK : V3(v.x, v.y, v.z);
-                traced++;
+                float4 o = line[N_LIGHT_O], d = line[N_LIGHT_D], v = line[N_LIGHT_VALUE];
+                rays += (unsigned)(__float_as_int(d.w) & 1);
+                if (o.w >= 0.f)
+                {
+                    Ray r;
+                    r.o = V3(o.x, o.y, o.z);
+                    r.d = V3(d.x, d.y, d.z);
+                    r.tmax = o.w;
+                    Ll = scene_any_hit(r) ? KYD_BLACK : V3(v.x, v.y, v.z);
+                    traced++;
+                }
             }
+            float3 e;
+            if (ds == KYD_DS_BOTH_MIS)
+                e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
+            else if (ds == KYD_DS_BSDF || ds == KYD_DS_BSDF_MIS)
+                e = Lb;
+            else
+                e = Ll;
+            line[N_RESULT] = make_float4(e.x, e.y, e.z, 0.f);
+            line[N_RESULT_PAD] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float3 e;
-        if (ds == KYD_DS_BOTH_MIS)
-            e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
-        else if (ds == KYD_DS_BSDF || ds == KYD_DS_BSDF_MIS)
-            e = Lb;
-        else
-            e = Ll;
-        w.nee_result[(long long)l * wp.plane + slot] = make_float4(e.x, e.y, e.z, 0.f);
     }
     flush_counters(rays, traced, counters);
 }
@@ -372,27 +513,16 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, co
 __global__ void __launch_bounds__(256) k_accumulate(WaveParams wp, WaveBuffers w, float* __restrict__ film)
 {
     const int stride = gridDim.x * blockDim.x;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < wp.npix; p += stride)
+    for (int px = blockIdx.x * blockDim.x + threadIdx.x; px < wp.npix; px += stride)
     {
-        float* o = film + 3 * (size_t)(wp.pixel_begin + p);
+        float* o = film + 3 * (size_t)(wp.pixel_begin + px);
         float3 L = V3(o[0], o[1], o[2]);
         for (int s = 0; s < wp.nspp; ++s)
         {
-            const int slot = s * wp.npix + p;
-            float4 L4 = w.radiance[slot];
-            float3 Li = V3(L4.x, L4.y, L4.z);
-            float4 vb = w.vx_beta[slot];
-            const int pending = __float_as_int(vb.w);
-            if (pending > 0)
-            {
-                float3 Ld = KYD_BLACK;
-                for (int l = 0; l < pending; ++l)
-                {
-                    float4 e = w.nee_result[(long long)l * wp.plane + slot];
-                    Ld = add(Ld, V3(e.x, e.y, e.z));
-                }
-                Li = add(Li, cmulc(V3(vb.x, vb.y, vb.z), Ld));
-            }
+            const int slot = s * wp.npix + px;
+            const float4* p = path_line(w, slot);
+            float4 L4 = p[P_RADIANCE];
+            float3 Li = add_pending(w, wp.plane, slot, p[P_VERTEX_BETA], V3(L4.x, L4.y, L4.z));
             L = add(L, mul(Li, wp.rp.weight));
         }
         o[0] = L.x; o[1] = L.y; o[2] = L.z;

@@ -27,7 +27,8 @@ def _assert_same(got, want, what):
 
 # kernel organisations: the split wavefront (default), the same with waves far smaller than the film
 # (several tiles, or several samples per wave), and the per-pixel kernel
-MODES = {"wavefront": (0, 0), "wavefront_small_waves": (0, 1000), "wavefront_multi_spp": (0, cases.W * cases.H * 3), "pixel": (ky.FLAG_FUSED, 0)}
+MODES = {"wavefront": (0, 0), "wavefront_small_waves": (0, 1000), "wavefront_multi_spp": (0, cases.W * cases.H * 3),
+         "wavefront_split_light_sample": (ky.FLAG_SPLIT_LIGHT_SAMPLE, 0), "pixel": (ky.FLAG_FUSED, 0)}
 
 
 @pytest.mark.parametrize("mode", list(MODES))
