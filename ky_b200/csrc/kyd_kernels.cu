@@ -477,8 +477,11 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                     k_intersect<true><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
                 else
                     k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
-                k_shade<<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
-                *launches += 2;
+                k_shade<LOBE_LAMBERT><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
+                k_shade<LOBE_PHONG><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
+                k_shade<LOBE_MIRROR><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
+                k_shade<LOBE_FRESNEL><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
+                *launches += 5;
                 if (nee)
                 {
                     if (wp.split_light_sample)

@@ -38,6 +38,10 @@ namespace kyd {
 enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong) */, Q_LOBE0 = 4 /* + 4 * parity + lobe */ };
 enum { FLAG_PREV_SPECULAR = 1 };
 
+#ifndef KYD_SHADE_MIN_BLOCKS
+#define KYD_SHADE_MIN_BLOCKS 4
+#endif
+
 // float4 units of a path line / a light-sampling line
 enum { P_ORIGIN = 0, P_DIRECTION = 1, P_BETA = 2, P_RADIANCE = 3, P_VERTEX_BETA = 4, P_RNG = 5, P_HIT = 6, P_HIT_PAD = 7, PATH_UNITS = 8 };
 enum { N_BSDF_O = 0, N_BSDF_D = 1, N_BSDF_VALUE = 2, N_LIGHT_O = 3, N_LIGHT_D = 4, N_LIGHT_VALUE = 5, N_RESULT = 6, N_RESULT_PAD = 7, NEE_UNITS = 8 };
@@ -395,12 +399,12 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     }
 }
 
-__global__ void __launch_bounds__(128) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
+// one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
+// shades most vertices, does not pay for Phong's pow() or the dielectric's Fresnel terms)
+template <int LOBE>
+__global__ void __launch_bounds__(128, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
-    shade_queue<LOBE_LAMBERT>(wp, w, counters, bounce);
-    shade_queue<LOBE_PHONG>(wp, w, counters, bounce);
-    shade_queue<LOBE_MIRROR>(wp, w, counters, bounce);
-    shade_queue<LOBE_FRESNEL>(wp, w, counters, bounce);
+    shade_queue<LOBE>(wp, w, counters, bounce);
 }
 
 // ---- light-sample as its own stage (KYD_FLAG_SPLIT_LIGHT_SAMPLE): one thread per (vertex, light) -------------
