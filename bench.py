@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--wave-paths", type=int, default=0, help="paths per wavefront (0 = library default)")
+    ap.add_argument("--direct-sample", default="both_mis", choices=["idle", "bsdf", "light", "bsdf_mis", "light_mis", "both_mis"],
+                    help="direct_sample_enum_t of the workload (the headline workload is both_mis; others are diagnostics)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -144,6 +146,8 @@ def main():
     import torch
     import torch.distributed as dist
     import ky_b200 as ky
+    DS = {"idle": ky.DS_IDLE, "bsdf": ky.DS_BSDF, "light": ky.DS_LIGHT, "bsdf_mis": ky.DS_BSDF_MIS, "light_mis": ky.DS_LIGHT_MIS,
+          "both_mis": ky.DS_BOTH_MIS}[args.direct_sample]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -167,7 +171,7 @@ def main():
 
     def step(k):
         b = base + (k * S) % max(S, share - S + 1)
-        d = ky.render_desc(WIDTH, HEIGHT, JOB_SPP, integrator=ky.INT_PT_ITERATION, max_depth=DEPTH, direct_sample=ky.DS_BOTH_MIS,
+        d = ky.render_desc(WIDTH, HEIGHT, JOB_SPP, integrator=ky.INT_PT_ITERATION, max_depth=DEPTH, direct_sample=DS,
                            sample_begin=b, sample_end=b + S, flags=ky.FLAG_ACCUMULATE | mode_flags)
         dev.render_device(d, film.data_ptr(), stream)
 
@@ -191,6 +195,7 @@ def main():
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     launches = rays = traced = 0
+    stage_ms = [0.0] * 8
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations, outside the per-step events
         ev[k][0].record()
@@ -200,6 +205,8 @@ def main():
         launches += st.kernel_launches
         rays += st.rays
         traced += st.rays_traced
+        for j in range(8):
+            stage_ms[j] += st.stage_ms[j]
     # the job's last act: one reduce of the partial films over NVLink, clamp on the root
     ev[-1][0].record()
     if world > 1:
@@ -229,7 +236,7 @@ def main():
 
     def e2e_step(k):
         b = base + (k * S) % max(S, share - S + 1)
-        d = ky.render_desc(WIDTH, HEIGHT, JOB_SPP, integrator=ky.INT_PT_ITERATION, max_depth=DEPTH, direct_sample=ky.DS_BOTH_MIS,
+        d = ky.render_desc(WIDTH, HEIGHT, JOB_SPP, integrator=ky.INT_PT_ITERATION, max_depth=DEPTH, direct_sample=DS,
                            sample_begin=b, sample_end=b + S, flags=ky.FLAG_CLAMP | mode_flags)
         dev.upload(scene)            # host->device: the flattened scene + request
         dev.render(d, host_film)     # device->host: the film
@@ -256,7 +263,7 @@ def main():
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"C5 cornell default_scene {WIDTH}x{HEIGHT}, path_tracing_iteration depth {DEPTH} both_mis, job {JOB_SPP} spp; "
+            "config": {"workload": f"C5 cornell default_scene {WIDTH}x{HEIGHT}, path_tracing_iteration depth {DEPTH} {args.direct_sample}, job {JOB_SPP} spp; "
                                    f"step = {S} spp slice per GPU (sample-index split across GPUs, one NCCL film reduce + clamp at the end)",
                        "mode": args.mode, "wave_paths": args.wave_paths, "l2": "flushed between timed steps (256 MiB write); each step also renders new sample indices",
                        "parallelism": f"spp-split x{world}"},
@@ -264,6 +271,8 @@ def main():
             "mrays_traced_per_s": traced_all / (total_ms * 1e-3) / 1e6,
             "rays_per_sample": rays_all / samples,
             "reduce_ms": reduce_ms,
+            "stage_ms_per_step": ({n: stage_ms[j] / args.steps for j, n in enumerate(["raygen", "intersect", "shade", "light_sample", "shadow", "-", "accumulate", "pixel"]) if stage_ms[j] > 0}
+                                  if os.environ.get("KYD_STAGE_TIMING") == "1" else None),
             "gpu_launches": int(launches_all),
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": WIDTH * HEIGHT * 3 * 4,

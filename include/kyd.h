@@ -208,6 +208,12 @@ int kyd_clamp_device(kyd_ctx* ctx, float* film_rgb_device, int64_t n, void* cuda
 
 int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out);
 
+/* device self-tests of exactness-critical fast paths.  KYD_SELFTEST_RSQRT: compares the FP32 fast path of
+   vec3 normalize's reciprocal square root with its definition (float)(1.0 / sqrt((double)s)), ky.cpp:314, for
+   the `count` float bit patterns starting at `first`; out2[0] = mismatches, out2[1] = inputs that took the slow path */
+enum kyd_selftest_kind { KYD_SELFTEST_RSQRT = 0 };
+int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2);
+
 /* size in paths of one wavefront (0 = choose from the film size); tuning knob, results do not depend on it */
 int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths);
 

@@ -91,14 +91,15 @@ class EntryParams(C.Structure):
 
 
 KYD_SYMBOLS = ["kyd_create", "kyd_destroy", "kyd_last_error", "kyd_upload_scene", "kyd_render",
-               "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths"]
+               "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest"]
 
 _kyd = None
 _host = None
 
 
 def kyd_path():
-    return os.path.join(LIB_DIR, "libkyd.so")
+    # KYD_LIB: an alternative build of the CUDA library (A/B measurements of kernel variants)
+    return os.environ.get("KYD_LIB") or os.path.join(LIB_DIR, "libkyd.so")
 
 
 def host_path():
@@ -123,6 +124,7 @@ def kyd():
         l.kyd_clamp_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         l.kyd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         l.kyd_set_wave_paths.argtypes = [C.c_void_p, C.c_int64]
+        l.kyd_selftest.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
         _kyd = l
     return _kyd
 
@@ -252,6 +254,11 @@ class Device:
 
     def set_wave_paths(self, paths):
         self._check(kyd().kyd_set_wave_paths(self._ctx, paths))
+
+    def selftest(self, which, first, count):
+        out = (C.c_uint64 * 2)()
+        self._check(kyd().kyd_selftest(self._ctx, which, first, count, out))
+        return int(out[0]), int(out[1])
 
     def stats(self):
         s = Stats()

@@ -1,5 +1,6 @@
 // kyd_api.cu -- the C ABI of include/kyd.h: context, scene upload, render orchestration.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -32,6 +33,8 @@ struct kyd_ctx
 
     WaveBuffers wave;
     int64_t wave_paths = 0;
+    bool stage_timing = false; // KYD_STAGE_TIMING=1: per-stage CUDA-event times in kyd_stats::stage_ms
+    StageTimer timer;
 };
 
 namespace {
@@ -169,7 +172,9 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         if (capacity > job) capacity = job;
         if (capacity < 1024) capacity = 1024;
         KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, ctx->scene.n_lights));
-        launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches);
+        ctx->timer.stream = stream;
+        launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches,
+                                ctx->stage_timing ? &ctx->timer : nullptr);
     }
     else
     {
@@ -191,7 +196,7 @@ void finish_stats(kyd_ctx* ctx, bool timed)
 {
     ctx->stats.rays = ctx->counters_pinned->rays;
     ctx->stats.rays_traced = ctx->counters_pinned->rays_traced;
-    ctx->stats.stage_ms[7] = 0;
+    if (ctx->stage_timing) ctx->timer.collect(ctx->stats.stage_ms);
     if (timed)
     {
         float ms = 0;
@@ -226,6 +231,7 @@ int kyd_create(kyd_ctx** out_ctx, int device)
     if ((e = cudaMalloc(&ctx->counters_dev, sizeof(DevCounters))) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaMallocHost(&ctx->counters_pinned, sizeof(DevCounters))) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     memset(ctx->counters_pinned, 0, sizeof(DevCounters));
+    { const char* e = getenv("KYD_STAGE_TIMING"); ctx->stage_timing = e && e[0] == '1'; }
     *out_ctx = ctx;
     return KYD_OK;
 }
@@ -384,6 +390,25 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out)
     cudaDeviceSynchronize();
     finish_stats(ctx, true);
     *out = ctx->stats;
+    return KYD_OK;
+}
+
+int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2)
+{
+    if (!ctx || !out2) return KYD_ERR_INVALID;
+    if (which != KYD_SELFTEST_RSQRT) return fail(ctx, KYD_ERR_INVALID, "unknown self-test");
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long* dev = nullptr;
+    KYD_CUDA(ctx, cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
+    cudaMemsetAsync(dev, 0, 2 * sizeof(unsigned long long), ctx->stream);
+    launch_selftest_rsqrt(first, count, dev, ctx->stream);
+    unsigned long long host[2] = { 0, 0 };
+    cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev);
+    KYD_CUDA(ctx, e);
+    out2[0] = host[0];
+    out2[1] = host[1];
     return KYD_OK;
 }
 

@@ -22,6 +22,13 @@
 namespace kyd {
 
 #define KYD_DEV __device__ __forceinline__
+// the double-precision libm bodies are hundreds of instructions each and have many call sites: kept out of
+// line so that the shading kernels stay closer to the instruction cache (KYD_MATH_INLINE=1 inlines them)
+#if defined(KYD_MATH_INLINE) && KYD_MATH_INLINE
+#define KYD_MATH __device__ __forceinline__
+#else
+#define KYD_MATH __device__ __noinline__
+#endif
 
 // the scene of the context that launched the kernel.  This header is included by exactly one
 // translation unit (kyd_kernels.cu), which therefore owns the symbol.
@@ -43,17 +50,17 @@ KYD_DEV float max_std(float a, float b) { return (a < b) ? b : a; }
 KYD_DEV float clamp_std(float v, float lo, float hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
 
 // libm contract
-KYD_DEV float cr_sin(float x) { return __double2float_rn(sin((double)x)); }
-KYD_DEV float cr_cos(float x) { return __double2float_rn(cos((double)x)); }
-KYD_DEV void cr_sincos(float x, float* s, float* c)
+KYD_MATH float cr_sin(float x) { return __double2float_rn(sin((double)x)); }
+KYD_MATH float cr_cos(float x) { return __double2float_rn(cos((double)x)); }
+KYD_MATH void cr_sincos(float x, float* s, float* c)
 {
     double ds, dc;
     sincos((double)x, &ds, &dc);
     *s = __double2float_rn(ds);
     *c = __double2float_rn(dc);
 }
-KYD_DEV float cr_acos(float x) { return __double2float_rn(acos((double)x)); }
-KYD_DEV float cr_pow(float x, float y) { return __double2float_rn(pow((double)x, (double)y)); }
+KYD_MATH float cr_acos(float x) { return __double2float_rn(acos((double)x)); }
+KYD_MATH float cr_pow(float x, float y) { return __double2float_rn(pow((double)x, (double)y)); }
 
 // ---- vectors (ky.cpp:226-388) -----------------------------------------------------------------------
 KYD_DEV float3 V3(float x, float y, float z) { return make_float3(x, y, z); }
@@ -68,8 +75,39 @@ KYD_DEV float3 cross(float3 a, float3 v)
 {
     return V3(a.y * v.z - a.z * v.y, a.z * v.x - a.x * v.z, a.x * v.y - a.y * v.x);
 }
-// ky.cpp:314
-KYD_DEV float rsqrt_ky(float s) { return __double2float_rn(__drcp_rn(__dsqrt_rn((double)s))); }
+// ky.cpp:314: (float)(1.0 / sqrt((double)s)) -- the definition, used as the slow path
+KYD_MATH float rsqrt_ky_reference(float s) { return __double2float_rn(__drcp_rn(__dsqrt_rn((double)s))); }
+
+// The same value without FP64 on the fast path.  Let y* = s^-1/2 exactly; the definition above is
+// RN32(p) with |p / y* - 1| <= 2^-51.9 (two correctly rounded double operations).
+//   y0  = MUFU seed, |y0 / y* - 1| <= 2^-22.9 (PTX rsqrt.approx.f32)
+//   r2  = 1 - s y0^2 to ~2^-46 absolute: t + tl = s y0 exactly (FMA), then two more FMAs
+//   yt  = y0 (1 + r2 / 2): one Newton step; |yt / y* - 1| <= 3/8 r2^2 + 2^-45 < 2^-44
+//   yh  = RN32(yt), rho = yt - yh (|rho| <= half an ulp of yh, computed with one FMA)
+// If rho stays 2^-14 of a half-ulp clear of the rounding boundary (2^-39 relative, 32x the error budget)
+// and yh is not a power of two (asymmetric interval), RN32(p) == yh.  Otherwise (6e-5 of calls), and for
+// zero / denormal / huge / non-finite s, the definition is evaluated.  Verified for every float bit
+// pattern by kyd_selftest (tests/test_gpu_parity.py::test_fast_rsqrt_is_exact_for_every_float).
+KYD_DEV float rsqrt_ky(float s)
+{
+#if defined(KYD_FAST_RSQRT) && !KYD_FAST_RSQRT
+    return __double2float_rn(__drcp_rn(__dsqrt_rn((double)s)));
+#endif
+    float y0;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(s));
+    const float t = __fmul_rn(s, y0);
+    const float tl = __fmaf_rn(s, y0, -t);
+    const float r = __fmaf_rn(-t, y0, 1.0f);
+    const float r2 = __fmaf_rn(-tl, y0, r);
+    const float h = __fmul_rn(0.5f, r2);
+    const float yh = __fmaf_rn(y0, h, y0);
+    const float rho = __fmaf_rn(y0, h, __fsub_rn(y0, yh));
+    const unsigned yb = __float_as_uint(yh);
+    const float half_ulp = __uint_as_float((yb & 0x7f800000u) - (24u << 23));
+    if (s > 0x1p-60f && s < 0x1p60f && fabsf(rho) < __fmul_rn(half_ulp, 0.99993896484375f) && (yb & 0x007fffffu) != 0u)
+        return yh;
+    return rsqrt_ky_reference(s);
+}
 KYD_DEV float3 normalize(float3 a) { return mul(a, rsqrt_ky(a.x * a.x + a.y * a.y + a.z * a.z)); }
 KYD_DEV float abs_dot(float3 a, float3 b) { return fabsf(dot(a, b)); }
 KYD_DEV float distance_sq(float3 a, float3 b) { return msq(sub(a, b)); }

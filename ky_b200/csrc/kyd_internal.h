@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "kyd_scene.h"
 
 namespace kyd {
@@ -32,6 +34,20 @@ struct WaveBuffers
     int* queue_nee[2] = {};        // vertices that sample lights: Lambert, Phong
 };
 
+// optional per-stage device timing (KYD_STAGE_TIMING=1): CUDA events around every kernel of the wavefront
+struct StageTimer
+{
+    enum { RAYGEN = 0, INTERSECT = 1, SHADE = 2, LIGHT_SAMPLE = 3, SHADOW = 4, ACCUMULATE = 6, PIXEL = 7 };
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events; // pairs
+    std::vector<int> stages;
+    size_t used = 0;
+    void begin(int stage);
+    void end();
+    void collect(double* stage_ms); // synchronises
+    ~StageTimer();
+};
+
 void upload_scene_constant(const DevScene& scene, cudaStream_t stream);
 
 // megakernel path: one thread per pixel, samples in order (used for every integrator; the only path
@@ -40,12 +56,14 @@ void launch_render_pixels(const RenderParams& rp, float* film_dev, DevCounters* 
 
 void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 
+void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
+
 void free_wave_buffers(WaveBuffers& w);
 // (re)allocates the wavefront buffers for `capacity` path slots and `lights` lights; returns a cudaError_t
 int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights);
 
 // wavefront path: path_tracing_iteration_t and direct_lighting_t.  Adds to `launches` the kernels it launched.
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
-                             cudaStream_t stream, int sm_count, uint64_t* launches);
+                             cudaStream_t stream, int sm_count, uint64_t* launches, StageTimer* timer);
 
 } // namespace kyd

@@ -387,7 +387,77 @@ void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream)
     k_clamp<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(film_dev, n);
 }
 
+// ---- self-tests of the exactness-critical fast paths ---------------------------------------------------
+// out[0] = bit patterns whose fast result differs from the definition, out[1] = patterns that took the slow path
+__global__ void k_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* __restrict__ out)
+{
+    unsigned long long bad = 0, slow = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    {
+        const float s = __uint_as_float((unsigned)(first + i));
+        const float want = rsqrt_ky_reference(s);
+        const float got = rsqrt_ky(s);
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got))
+            ++bad;
+        // recompute the acceptance test's outcome: the slow path is taken exactly when the seed-based value is rejected
+        float y0;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(s));
+        const float t = __fmul_rn(s, y0), tl = __fmaf_rn(s, y0, -t);
+        const float r2 = __fmaf_rn(-tl, y0, __fmaf_rn(-t, y0, 1.0f));
+        const float h = __fmul_rn(0.5f, r2), yh = __fmaf_rn(y0, h, y0);
+        const float rho = __fmaf_rn(y0, h, __fsub_rn(y0, yh));
+        const unsigned yb = __float_as_uint(yh);
+        const float half_ulp = __uint_as_float((yb & 0x7f800000u) - (24u << 23));
+        if (!(s > 0x1p-60f && s < 0x1p60f && fabsf(rho) < __fmul_rn(half_ulp, 0.99993896484375f) && (yb & 0x007fffffu) != 0u))
+            ++slow;
+    }
+    if (bad) atomicAdd(&out[0], bad);
+    if (slow) atomicAdd(&out[1], slow);
+}
+
+void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream)
+{
+    k_selftest_rsqrt<<<148 * 16, 256, 0, stream>>>(first, count, out_dev);
+}
+
 // ---- wavefront orchestration ---------------------------------------------------------------------------
+void StageTimer::begin(int stage)
+{
+    if (used + 2 > events.size())
+    {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        events.push_back(a);
+        events.push_back(b);
+    }
+    stages.resize(events.size() / 2);
+    stages[used / 2] = stage;
+    cudaEventRecord(events[used], stream);
+}
+void StageTimer::end()
+{
+    cudaEventRecord(events[used + 1], stream);
+    used += 2;
+}
+void StageTimer::collect(double* stage_ms)
+{
+    if (used == 0) return;
+    cudaEventSynchronize(events[used - 1]);
+    for (size_t k = 0; k < used; k += 2)
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, events[k], events[k + 1]);
+        stage_ms[stages[k / 2]] += ms;
+    }
+    used = 0;
+}
+StageTimer::~StageTimer()
+{
+    for (cudaEvent_t e : events) cudaEventDestroy(e);
+}
+
 template <class T>
 static cudaError_t alloc_array(T** p, size_t count)
 {
@@ -431,8 +501,9 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
 }
 
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
-                             cudaStream_t stream, int sm_count, uint64_t* launches)
+                             cudaStream_t stream, int sm_count, uint64_t* launches, StageTimer* timer)
 {
+    auto T = [&](int stage) { if (timer) { if (stage >= 0) timer->begin(stage); else timer->end(); } };
     const long long npix_total = (long long)rp.width * rp.height;
     const int nsamples = rp.sample_end - rp.sample_begin;
     const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
@@ -469,31 +540,43 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.direct_only = direct_only ? 1 : 0;
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
 
+            T(StageTimer::RAYGEN);
             k_raygen<<<grid256, 256, 0, stream>>>(wp, w, counters);
+            T(-1);
             ++*launches;
             for (int bounce = 0; bounce <= last_bounce; ++bounce)
             {
+                T(StageTimer::INTERSECT);
                 if (bounce == 0)
                     k_intersect<true><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
                 else
                     k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
+                T(-1);
+                T(StageTimer::SHADE);
                 k_shade<LOBE_LAMBERT><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
                 k_shade<LOBE_PHONG><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
                 k_shade<LOBE_MIRROR><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
                 k_shade<LOBE_FRESNEL><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
+                T(-1);
                 *launches += 5;
                 if (nee)
                 {
                     if (wp.split_light_sample)
                     {
+                        T(StageTimer::LIGHT_SAMPLE);
                         k_light_sample<<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        T(-1);
                         ++*launches;
                     }
+                    T(StageTimer::SHADOW);
                     k_shadow<<<grid256, 256, 0, stream>>>(wp, w, counters);
+                    T(-1);
                     ++*launches;
                 }
             }
+            T(StageTimer::ACCUMULATE);
             k_accumulate<<<grid256, 256, 0, stream>>>(wp, w, film_dev);
+            T(-1);
             ++*launches;
         }
     }

@@ -41,6 +41,7 @@ enum { FLAG_PREV_SPECULAR = 1 };
 #ifndef KYD_SHADE_MIN_BLOCKS
 #define KYD_SHADE_MIN_BLOCKS 4
 #endif
+#define SHADE_THREADS 128
 
 // float4 units of a path line / a light-sampling line
 enum { P_ORIGIN = 0, P_DIRECTION = 1, P_BETA = 2, P_RADIANCE = 3, P_VERTEX_BETA = 4, P_RNG = 5, P_HIT = 6, P_HIT_PAD = 7, PATH_UNITS = 8 };
@@ -93,11 +94,62 @@ KYD_DEV void queue_push(bool pred, int value, int* __restrict__ queue, unsigned 
         queue[base + __popc(mask & ((1u << lane) - 1))] = value;
 }
 
+// Pushes into up to NQ queues with ONE round of atomics per warp and iteration (lane q issues queue q's
+// atomic, so the NQ atomics are in flight together) whose latency is hidden: reserve() issues them and
+// commit(), called one loop iteration later, reads the returned bases and writes the entries.  In the first
+// per-lobe version 61 % of k_intersect's stall samples were lanes waiting for these atomics
+// (profiles/r01_wave_lines_stalls.txt).
+template <int NQ>
+struct WarpPush
+{
+    unsigned masks[NQ];        // ballots of the iteration whose entries are not written yet
+    unsigned long long base;   // lane q < NQ: first index reserved in queue q
+    int value;                 // this lane's entry
+    unsigned preds;            // bit q: this lane pushes `value` into queue q
+    bool pending;
+
+    KYD_DEV void init() { pending = false; preds = 0; value = 0; base = 0; }
+
+    KYD_DEV void reserve(unsigned preds_, int value_, unsigned long long* const (&tails)[NQ])
+    {
+        __syncwarp();
+        preds = preds_;
+        value = value_;
+        const int lane = threadIdx.x & 31;
+        base = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+        {
+            masks[q] = __ballot_sync(0xffffffffu, (preds_ >> q) & 1u);
+            if (lane == q && masks[q] != 0)
+                base = atomicAdd(tails[q], (unsigned long long)__popc(masks[q]));
+        }
+        pending = true;
+    }
+
+    KYD_DEV void commit(int* const (&queues)[NQ])
+    {
+        if (!pending) // warp-uniform
+            return;
+        __syncwarp();
+        const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+        {
+            const unsigned long long b = __shfl_sync(0xffffffffu, base, q);
+            if ((preds >> q) & 1u)
+                queues[q][b + __popc(masks[q] & lt)] = value;
+        }
+        pending = false;
+    }
+};
+
 KYD_DEV unsigned long long unpack_rng(float4 v) { return (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32); }
 KYD_DEV float4 pack_rng(unsigned long long s) { return make_float4(__uint_as_float((unsigned)s), __uint_as_float((unsigned)(s >> 32)), 0.f, 0.f); }
 
-// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576
-KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, float4 vb, float3 Lo)
+// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576.
+// first: the result of light 0 when the caller already fetched it (shade prefetches it with the path line)
+KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, float4 vb, float3 Lo, const float4* first = nullptr)
 {
     const int pending = __float_as_int(vb.w);
     if (pending > 0)
@@ -105,13 +157,24 @@ KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, floa
         float3 Ld = KYD_BLACK;
         for (int l = 0; l < pending; ++l)
         {
-            float4 e = nee_line(w, plane, l, slot)[N_RESULT];
+            float4 e = (l == 0 && first) ? *first : nee_line(w, plane, l, slot)[N_RESULT];
             Ld = add(Ld, V3(e.x, e.y, e.z));
         }
         Lo = add(Lo, cmulc(V3(vb.x, vb.y, vb.z), Ld));
     }
     return Lo;
 }
+
+// Ampere-style asynchronous 16-byte global -> shared copies (LDGSTS): the gather of the NEXT path's line
+// is in flight while the current path is shaded, at no register cost
+KYD_DEV void cp_async16(void* smem, const void* gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+KYD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+KYD_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ---- raygen: camera_t::generate_ray for every slot of the wave (ky.cpp:3714-3715) ----------------------
 __global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
@@ -164,7 +227,11 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
         counters->queue[which[threadIdx.x]] = 0;
     }
     const int* __restrict__ queue = parity ? w.queue_b : w.queue_a;
-    unsigned long long* tails = &counters->queue[Q_LOBE0 + 4 * parity];
+    unsigned long long* const tails[4] = { &counters->queue[Q_LOBE0 + 4 * parity], &counters->queue[Q_LOBE0 + 4 * parity + 1],
+                                           &counters->queue[Q_LOBE0 + 4 * parity + 2], &counters->queue[Q_LOBE0 + 4 * parity + 3] };
+    int* const lobe_queues[4] = { w.queue_lobe[0], w.queue_lobe[1], w.queue_lobe[2], w.queue_lobe[3] };
+    WarpPush<4> push;
+    push.init();
     const bool has_env = c_scene.env_light >= 0;
     const int stride = gridDim.x * blockDim.x;
     unsigned rays = 0;
@@ -206,10 +273,10 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
                 }
             }
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            queue_push(lobe == c, slot, w.queue_lobe[c], &tails[c]);
+        push.commit(lobe_queues);                                  // the previous iteration's entries
+        push.reserve(lobe >= 0 ? (1u << lobe) : 0u, slot, tails);  // this iteration's atomics, consumed next time round
     }
+    push.commit(lobe_queues);
     flush_counters(rays, rays, counters);
 }
 
@@ -263,11 +330,15 @@ KYD_DEV void light_sample_pair(const WaveParams& wp, const WaveBuffers& w, const
 }
 
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
-template <int LOBE>
-KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee)
+// pre / PRE_STRIDE: where the path line's units are read from -- the line itself (stride 1) or this thread's
+// column of the shared-memory prefetch buffer; pre_result0: light 0's pending estimator value
+template <int LOBE, int PRE_STRIDE>
+KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, const float4* pre, const float4* pre_result0, int slot, int bounce, int n_lights,
+                          bool* out_alive, bool* out_nee)
 {
     float4* p = path_line(w, slot);
-    float4 o4 = p[P_ORIGIN], d4 = p[P_DIRECTION], b4 = p[P_BETA], L4 = p[P_RADIANCE], vb = p[P_VERTEX_BETA], rng4 = p[P_RNG], h = p[P_HIT];
+    float4 o4 = pre[P_ORIGIN * PRE_STRIDE], d4 = pre[P_DIRECTION * PRE_STRIDE], b4 = pre[P_BETA * PRE_STRIDE], L4 = pre[P_RADIANCE * PRE_STRIDE];
+    float4 vb = pre[P_VERTEX_BETA * PRE_STRIDE], rng4 = pre[P_RNG * PRE_STRIDE], h = pre[P_HIT * PRE_STRIDE], res0 = *pre_result0;
     Ray r;
     r.o = V3(o4.x, o4.y, o4.z);
     r.d = V3(d4.x, d4.y, d4.z);
@@ -277,7 +348,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     const int surface = __float_as_int(h.y);
 
     // light gathered at the previous vertex (see file header)
-    float3 Lo = add_pending(w, wp.plane, slot, vb, V3(L4.x, L4.y, L4.z));
+    float3 Lo = add_pending(w, wp.plane, slot, vb, V3(L4.x, L4.y, L4.z), &res0);
     int new_pending = 0;
 
     HitGeom g = shape_hit_geom(c_scene.surf_shape[surface], r, h.x);
@@ -372,6 +443,16 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     p[P_RNG] = pack_rng(rng_state);
 }
 
+// gathers one path line (units 0..6) and light 0's pending result into this thread's prefetch column
+KYD_DEV void prefetch_path(const WaveParams& wp, const WaveBuffers& w, float4* column, int slot)
+{
+    const float4* p = path_line(w, slot);
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+        cp_async16(column + k * SHADE_THREADS, p + k);
+    cp_async16(column + 7 * SHADE_THREADS, nee_line(w, wp.plane, 0, slot) + N_RESULT);
+}
+
 template <int LOBE>
 KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
 {
@@ -381,28 +462,69 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     int* __restrict__ next_queue = parity ? w.queue_a : w.queue_b;
     const int stride = gridDim.x * blockDim.x;
     const int n_lights = c_scene.n_lights;
-    const int base_i = blockIdx.x * blockDim.x + threadIdx.x;
-    // whole warps iterate together so that the ballots in queue_push are convergent
-    for (int i0 = base_i - (threadIdx.x & 31); i0 < n; i0 += stride)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // queue 0: the next bounce's rays; queue 1: vertices whose light queries the shadow stage resolves
+    unsigned long long* const tails[2] = { &counters->queue[Q_RAY0 + (parity ^ 1)], &counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)] };
+    int* const out_queues[2] = { next_queue, w.queue_nee[LOBE == LOBE_PHONG] };
+    WarpPush<2> push;
+    push.init();
+
+#if !defined(KYD_PREFETCH) || !KYD_PREFETCH
+    // default: the line is copied synchronously (KYD_PREFETCH=1 selects the cp.async double-buffered gather
+    // below, which measured 6 % slower: profiles/r01_ab_variants.txt)
+    for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, i += stride)
     {
-        const int i = i0 + (threadIdx.x & 31);
         bool alive = false, wants_nee = false;
         int slot = 0;
         if (i < n)
         {
             slot = queue[i];
-            shade_vertex<LOBE>(wp, w, slot, bounce, n_lights, &alive, &wants_nee);
+            shade_vertex<LOBE, 1>(wp, w, path_line(w, slot), nee_line(w, wp.plane, 0, slot) + N_RESULT, slot, bounce, n_lights, &alive, &wants_nee);
         }
-        queue_push(alive, slot, next_queue, &counters->queue[Q_RAY0 + (parity ^ 1)]);
-        if (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG)
-            queue_push(wants_nee, slot, w.queue_nee[LOBE == LOBE_PHONG], &counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)]);
+        push.commit(out_queues);
+        push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
     }
+    push.commit(out_queues);
+    return;
+#else
+    // [buffer][unit][thread]: consecutive threads touch consecutive 16-byte words (no bank conflicts); a
+    // thread only ever reads the column it filled itself, so cp.async.wait_group is all the ordering needed
+    __shared__ float4 s_pre[2][8][SHADE_THREADS];
+    int slot_cur = i < n ? queue[i] : -1;
+    int slot_next = (i + stride < n && i + stride >= 0) ? queue[i + stride] : -1;
+    if (slot_cur >= 0)
+        prefetch_path(wp, w, &s_pre[0][0][threadIdx.x], slot_cur);
+    cp_async_commit();
+
+    // whole warps iterate together so that the ballots in queue_push are convergent
+    int buf = 0;
+    for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, i += stride, buf ^= 1)
+    {
+        if (slot_next >= 0)
+            prefetch_path(wp, w, &s_pre[buf ^ 1][0][threadIdx.x], slot_next);
+        cp_async_commit();
+        const long long i2 = (long long)i + 2ll * stride;
+        const int slot_next2 = i2 < n ? queue[i2] : -1;
+        cp_async_wait<1>(); // everything but the newest group has landed: this iteration's line is in shared memory
+
+        bool alive = false, wants_nee = false;
+        const int slot = slot_cur < 0 ? 0 : slot_cur;
+        if (slot_cur >= 0)
+            shade_vertex<LOBE, SHADE_THREADS>(wp, w, &s_pre[buf][0][threadIdx.x], &s_pre[buf][7][threadIdx.x], slot, bounce, n_lights, &alive, &wants_nee);
+        push.commit(out_queues);
+        push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
+        slot_cur = slot_next;
+        slot_next = slot_next2;
+    }
+    push.commit(out_queues);
+    cp_async_wait<0>();
+#endif
 }
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
 // shades most vertices, does not pay for Phong's pow() or the dielectric's Fresnel terms)
 template <int LOBE>
-__global__ void __launch_bounds__(128, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
+__global__ void __launch_bounds__(SHADE_THREADS, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
     shade_queue<LOBE>(wp, w, counters, bounce);
 }

@@ -74,6 +74,16 @@ def test_sample_ranges_and_device_film_accumulation(device, flags):
     _assert_same(whole, want, "one-shot film")
 
 
+def test_fast_rsqrt_is_exact_for_every_float(device):
+    """vec3 normalize's (float)(1.0 / sqrt((double)s)) (ky.cpp:314): the FP32 fast path equals the FP64 definition
+    for all 2^32 float bit patterns; only ~6e-5 of the in-range inputs need the FP64 slow path."""
+    bad, slow = device.selftest(0, 0, 1 << 32)
+    assert bad == 0
+    in_range = (int(np.float32(2.0 ** 60).view(np.uint32)) - int(np.float32(2.0 ** -60).view(np.uint32)))
+    outside = (1 << 32) - in_range
+    assert slow - outside < 2e-4 * in_range, (slow, outside)
+
+
 def test_debug_sampler(device):
     scene = cases.make_scene("cornell")
     desc = ky.render_desc(cases.W, cases.H, 2, sampler=ky.SAMPLER_DEBUG)
