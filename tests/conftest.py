@@ -19,6 +19,7 @@ def built():
     import __graft_entry__ as g
     g.build_kyd()
     g.build_host()
+    g.build_cli()
     g.build_oracle()
     return True
 
