@@ -84,10 +84,20 @@ KYD_MATH float rsqrt_ky_reference(float s) { return __double2float_rn(__drcp_rn(
 //   r2  = 1 - s y0^2 to ~2^-46 absolute: t + tl = s y0 exactly (FMA), then two more FMAs
 //   yt  = y0 (1 + r2 / 2): one Newton step; |yt / y* - 1| <= 3/8 r2^2 + 2^-45 < 2^-44
 //   yh  = RN32(yt), rho = yt - yh (|rho| <= half an ulp of yh, computed with one FMA)
-// If rho stays 2^-14 of a half-ulp clear of the rounding boundary (2^-39 relative, 32x the error budget)
-// and yh is not a power of two (asymmetric interval), RN32(p) == yh.  Otherwise (6e-5 of calls), and for
-// zero / denormal / huge / non-finite s, the definition is evaluated.  Verified for every float bit
+// If rho stays 2^-14 of a half-ulp clear of the rounding boundary (2^-39 relative, 32x the error budget),
+// RN32(p) == yh.  Below a power of two the float spacing halves, so there the lower boundary is half as far
+// (axis-aligned normals normalise to exactly 1.0: the common case in a Cornell box).  Otherwise (6e-5 of
+// calls), and for zero / denormal / huge / non-finite s, the definition is evaluated.  Verified for every float bit
 // pattern by kyd_selftest (tests/test_gpu_parity.py::test_fast_rsqrt_is_exact_for_every_float).
+KYD_DEV bool rsqrt_ky_accept(float s, float yh, float rho)
+{
+    const unsigned yb = __float_as_uint(yh);
+    const float half_ulp = __uint_as_float((yb & 0x7f800000u) - (24u << 23));
+    const float hi = __fmul_rn(half_ulp, 0.99993896484375f);
+    const float lo = (yb & 0x007fffffu) != 0u ? -hi : __fmul_rn(-0.5f, hi);
+    return s > 0x1p-60f && s < 0x1p60f && rho < hi && rho > lo;
+}
+
 KYD_DEV float rsqrt_ky(float s)
 {
 #if defined(KYD_FAST_RSQRT) && !KYD_FAST_RSQRT
@@ -102,9 +112,7 @@ KYD_DEV float rsqrt_ky(float s)
     const float h = __fmul_rn(0.5f, r2);
     const float yh = __fmaf_rn(y0, h, y0);
     const float rho = __fmaf_rn(y0, h, __fsub_rn(y0, yh));
-    const unsigned yb = __float_as_uint(yh);
-    const float half_ulp = __uint_as_float((yb & 0x7f800000u) - (24u << 23));
-    if (s > 0x1p-60f && s < 0x1p60f && fabsf(rho) < __fmul_rn(half_ulp, 0.99993896484375f) && (yb & 0x007fffffu) != 0u)
+    if (rsqrt_ky_accept(s, yh, rho))
         return yh;
     return rsqrt_ky_reference(s);
 }

@@ -24,9 +24,9 @@ struct WaveBuffers
     int64_t capacity = 0;
     int max_lights = 0;
     // layouts: kyd_wavefront.cuh
-    float4* path = nullptr;       // one 128-byte line (8 float4) per path slot
+    float4* path = nullptr;       // one 64-byte record (4 float4) per path slot
     float4* vertex = nullptr;     // 6 float4 per path slot: vertex record of the split light-sample stage
-    float4* nee = nullptr;        // one 128-byte line per (light, path slot): the two NEE queries and their result
+    float4* nee = nullptr;        // one 128-byte line per (light, path slot): the two NEE queries, vertex beta, result
     // queues of path slots
     int* queue_a = nullptr;        // ray queues (ping-pong by bounce parity)
     int* queue_b = nullptr;

@@ -407,9 +407,7 @@ __global__ void k_selftest_rsqrt(unsigned long long first, unsigned long long co
         const float r2 = __fmaf_rn(-tl, y0, __fmaf_rn(-t, y0, 1.0f));
         const float h = __fmul_rn(0.5f, r2), yh = __fmaf_rn(y0, h, y0);
         const float rho = __fmaf_rn(y0, h, __fsub_rn(y0, yh));
-        const unsigned yb = __float_as_uint(yh);
-        const float half_ulp = __uint_as_float((yb & 0x7f800000u) - (24u << 23));
-        if (!(s > 0x1p-60f && s < 0x1p60f && fabsf(rho) < __fmul_rn(half_ulp, 0.99993896484375f) && (yb & 0x007fffffu) != 0u))
+        if (!rsqrt_ky_accept(s, yh, rho))
             ++slow;
     }
     if (bad) atomicAdd(&out[0], bad);
@@ -484,7 +482,7 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
     const size_t P = (size_t)capacity, L = (size_t)lights;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-    ok(alloc_array(&w.path, 8 * P));
+    ok(alloc_array(&w.path, 4 * P));
     ok(alloc_array(&w.vertex, 6 * P));
     ok(alloc_array(&w.nee, 8 * L * P));
     ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P));

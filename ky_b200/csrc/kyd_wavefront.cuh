@@ -9,19 +9,24 @@
 // Divergence control (profiles/r01_wave1M_*: the first version ran shade at 11 of 32 lanes): the intersect
 // stage sorts the paths it hit by the BSDF lobe they will be shaded with (Lambert / Phong / mirror / glass;
 // a plastic surface picks its lobe with a hash of the hit, so the lobe is known there) into one queue per
-// lobe.  Shade and light-sample walk the queues one lobe after the other with lobe-specialised code, so a
-// warp never mixes lobes.  Paths that miss the scene are finished inside intersect.
+// lobe.  Shade runs once per lobe with lobe-specialised code, so a warp never mixes lobes.  Paths that miss
+// the scene are finished inside intersect.
 //
-// Data layout (profiles/r01_wave_lobe_soa_*: lobe-sorted queues turn the state accesses into gathers, and
-// 16-byte SoA elements then waste half of every 32-byte DRAM sector): the state of a path is ONE 128-byte
-// line, fields grouped by the sector the stages touch together:
-//     sector 0   ray origin.xyz, tmax | ray direction.xyz, flags          intersect reads, shade rewrites
-//     sector 1   beta.rgb, - | Lo.rgb, -                                   shade
-//     sector 2   beta of the vertex that sampled lights .rgb, pending | rng state, -     shade, accumulate
-//     sector 3   hit distance, surface, -, - | -                          intersect writes, shade reads
-// and the light-sampling record of a (light, path) pair is one line: the BSDF-sampled query (origin, tmax |
-// direction, flag | value), the light-sampled query (same three), and the estimator's result.
-// Every stage reads and writes whole sectors.
+// Data layout.  Lobe-sorted queues turn the state accesses into gathers over gigabytes, and the shade stage
+// is bound by scattered-DRAM throughput: it moved ~2.4 TB/s whether it wrote light-sampling records (352 B
+// per vertex, 103 ms per step) or not (224 B, 64.5 ms) -- profiles/r01_ab_variants.txt.  So the records are
+// as small as whole 32-byte sectors allow:
+//   path line, 64 bytes:
+//     sector 0   origin.xyz, hit distance | direction.xyz, flags (previous vertex specular, pending light
+//                count, hit surface)                         intersect reads and rewrites it, shade rewrites it
+//     sector 1   beta.rgb, Lo.rgb, rng state (2 words)        shade
+//   light-sampling line of a (light, path) pair, 128 bytes of which 64 are normally touched:
+//     sector 0   light-sampled query: origin.xyz, tmax | direction.xyz, flags
+//     sector 1   its value.rgb, vertex beta.r | vertex beta.gb, BSDF-sampled query's value.rg
+//     sector 2   BSDF-sampled query: origin.xyz, tmax | direction.xyz, value.b    (only when that query is
+//                live: ~5 % of Cornell vertices, the rest have a zero light pdf)
+//     sector 3   the estimator's value.rgb | vertex beta.rgb                      (shadow writes, next shade reads)
+//   A vertex none of whose queries can contribute writes no light-sampling line and is not queued for shadow.
 //
 // Order of FP32 additions into a path's radiance Lo is the reference's: emitted light of a vertex, then
 // beta * Ld of that vertex (ky.cpp:4553-4576).  The Ld of a vertex becomes known one stage later than the
@@ -36,17 +41,21 @@ namespace kyd {
 
 // queue tails in DevCounters::queue
 enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong) */, Q_LOBE0 = 4 /* + 4 * parity + lobe */ };
-enum { FLAG_PREV_SPECULAR = 1 };
 
 #ifndef KYD_SHADE_MIN_BLOCKS
 #define KYD_SHADE_MIN_BLOCKS 4
 #endif
 #define SHADE_THREADS 128
 
-// float4 units of a path line / a light-sampling line
-enum { P_ORIGIN = 0, P_DIRECTION = 1, P_BETA = 2, P_RADIANCE = 3, P_VERTEX_BETA = 4, P_RNG = 5, P_HIT = 6, P_HIT_PAD = 7, PATH_UNITS = 8 };
-enum { N_BSDF_O = 0, N_BSDF_D = 1, N_BSDF_VALUE = 2, N_LIGHT_O = 3, N_LIGHT_D = 4, N_LIGHT_VALUE = 5, N_RESULT = 6, N_RESULT_PAD = 7, NEE_UNITS = 8 };
-enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_PAD = 5, VERTEX_UNITS = 6 };
+// float4 units of the records
+enum { P_ORIGIN = 0, P_DIRECTION = 1, P_BETA = 2, P_TAIL = 3, PATH_UNITS = 4 };
+enum { N_LIGHT_O = 0, N_LIGHT_D = 1, N_LIGHT_VALUE = 2, N_MIXED = 3, N_BSDF_O = 4, N_BSDF_D = 5, N_RESULT = 6, N_VERTEX_BETA = 7, NEE_UNITS = 8 };
+enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_BETA = 5, VERTEX_UNITS = 6 };
+
+// flags word of a path (w of the direction unit)
+enum { FLAG_PREV_SPECULAR = 1, FLAG_PENDING_SHIFT = 4, FLAG_PENDING_MASK = 0x1f << 4, FLAG_SURFACE_SHIFT = 12 };
+// flags word of a light-sampling line (w of the light query's direction unit)
+enum { NEE_REF_BSDF = 1, NEE_REF_LIGHT = 2, NEE_BSDF_LIVE = 4 };
 
 struct WaveParams
 {
@@ -75,30 +84,12 @@ KYD_DEV void flush_counters(unsigned rays, unsigned traced, DevCounters* counter
     }
 }
 
-// warp-aggregated push: one atomic per warp, ballot + popc prefix for the lane offsets.  Must be reached
-// by all 32 lanes; the __syncwarp() makes them arrive together (without it the lanes of a diverged warp
-// execute the ballot / shuffle group by group: 18 % of the first version's shade instructions).
-KYD_DEV void queue_push(bool pred, int value, int* __restrict__ queue, unsigned long long* __restrict__ tail)
-{
-    __syncwarp();
-    const unsigned mask = __ballot_sync(0xffffffffu, pred);
-    if (mask == 0)
-        return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    unsigned long long base = 0;
-    if (lane == leader)
-        base = atomicAdd(tail, (unsigned long long)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred)
-        queue[base + __popc(mask & ((1u << lane) - 1))] = value;
-}
-
-// Pushes into up to NQ queues with ONE round of atomics per warp and iteration (lane q issues queue q's
-// atomic, so the NQ atomics are in flight together) whose latency is hidden: reserve() issues them and
-// commit(), called one loop iteration later, reads the returned bases and writes the entries.  In the first
-// per-lobe version 61 % of k_intersect's stall samples were lanes waiting for these atomics
-// (profiles/r01_wave_lines_stalls.txt).
+// Pushes into up to NQ queues with ONE atomic instruction per warp and iteration (lane q reserves queue q's
+// range) whose latency is hidden: reserve() issues it and commit(), called one loop iteration later, reads
+// the returned bases and writes the entries.  History (profiles/r01_wave_lines_stalls.txt): one atomic per
+// queue with an immediate shuffle -> 61 % of k_intersect's stall samples were lanes waiting for atomics; NQ
+// predicated atomics into one destination register still serialise on that register; per-lane addresses in
+// one instruction do not.
 template <int NQ>
 struct WarpPush
 {
@@ -112,18 +103,25 @@ struct WarpPush
 
     KYD_DEV void reserve(unsigned preds_, int value_, unsigned long long* const (&tails)[NQ])
     {
-        __syncwarp();
+        __syncwarp(); // all 32 lanes arrive together: a diverged warp would execute the ballots group by group
         preds = preds_;
         value = value_;
         const int lane = threadIdx.x & 31;
-        base = 0;
+        unsigned my_count = 0;
+        unsigned long long* my_tail = tails[0];
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
         {
             masks[q] = __ballot_sync(0xffffffffu, (preds_ >> q) & 1u);
-            if (lane == q && masks[q] != 0)
-                base = atomicAdd(tails[q], (unsigned long long)__popc(masks[q]));
+            if (lane == q)
+            {
+                my_count = __popc(masks[q]);
+                my_tail = tails[q];
+            }
         }
+        base = 0;
+        if (lane < NQ && my_count != 0)
+            base = atomicAdd(my_tail, (unsigned long long)my_count);
         pending = true;
     }
 
@@ -144,37 +142,57 @@ struct WarpPush
     }
 };
 
-KYD_DEV unsigned long long unpack_rng(float4 v) { return (unsigned long long)__float_as_uint(v.x) | ((unsigned long long)__float_as_uint(v.y) << 32); }
-KYD_DEV float4 pack_rng(unsigned long long s) { return make_float4(__uint_as_float((unsigned)s), __uint_as_float((unsigned)(s >> 32)), 0.f, 0.f); }
-
-// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576.
-// first: the result of light 0 when the caller already fetched it (shade prefetches it with the path line)
-KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, float4 vb, float3 Lo, const float4* first = nullptr)
+// ---- path record ------------------------------------------------------------------------------------------
+struct PathState
 {
-    const int pending = __float_as_int(vb.w);
+    float3 o, d;
+    float t;                    // hit distance (after intersect)
+    int flags;
+    float3 beta, Lo;
+    unsigned long long rng;
+
+    KYD_DEV int pending() const { return (flags & FLAG_PENDING_MASK) >> FLAG_PENDING_SHIFT; }
+    KYD_DEV int surface() const { return (flags >> FLAG_SURFACE_SHIFT) - 1; }
+};
+
+KYD_DEV void unpack_path(PathState& s, float4 u0, float4 u1, float4 u2, float4 u3)
+{
+    s.o = V3(u0.x, u0.y, u0.z); s.t = u0.w;
+    s.d = V3(u1.x, u1.y, u1.z); s.flags = __float_as_int(u1.w);
+    s.beta = V3(u2.x, u2.y, u2.z);
+    s.Lo = V3(u2.w, u3.x, u3.y);
+    s.rng = (unsigned long long)__float_as_uint(u3.z) | ((unsigned long long)__float_as_uint(u3.w) << 32);
+}
+
+KYD_DEV void store_path_ray(float4* p, float3 o, float t, float3 d, int flags)
+{
+    p[P_ORIGIN] = make_float4(o.x, o.y, o.z, t);
+    p[P_DIRECTION] = make_float4(d.x, d.y, d.z, __int_as_float(flags));
+}
+
+KYD_DEV void store_path_tail(float4* p, float3 beta, float3 Lo, unsigned long long rng)
+{
+    p[P_BETA] = make_float4(beta.x, beta.y, beta.z, Lo.x);
+    p[P_TAIL] = make_float4(Lo.y, Lo.z, __uint_as_float((unsigned)rng), __uint_as_float((unsigned)(rng >> 32)));
+}
+
+// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576
+KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, int pending, float3 Lo)
+{
     if (pending > 0)
     {
-        float3 Ld = KYD_BLACK;
-        for (int l = 0; l < pending; ++l)
+        const float4* line0 = nee_line(w, plane, 0, slot);
+        float4 e0 = line0[N_RESULT], vb = line0[N_VERTEX_BETA];
+        float3 Ld = add(KYD_BLACK, V3(e0.x, e0.y, e0.z));
+        for (int l = 1; l < pending; ++l)
         {
-            float4 e = (l == 0 && first) ? *first : nee_line(w, plane, l, slot)[N_RESULT];
+            float4 e = nee_line(w, plane, l, slot)[N_RESULT];
             Ld = add(Ld, V3(e.x, e.y, e.z));
         }
         Lo = add(Lo, cmulc(V3(vb.x, vb.y, vb.z), Ld));
     }
     return Lo;
 }
-
-// Ampere-style asynchronous 16-byte global -> shared copies (LDGSTS): the gather of the NEXT path's line
-// is in flight while the current path is shaded, at no register cost
-KYD_DEV void cp_async16(void* smem, const void* gmem)
-{
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-KYD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-KYD_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ---- raygen: camera_t::generate_ray for every slot of the wave (ky.cpp:3714-3715) ----------------------
 __global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
@@ -190,12 +208,8 @@ __global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, De
         float2 jitter = smp.get_float2();
         Ray r = generate_ray((float)x + jitter.x, (float)y + jitter.y);
         float4* p = path_line(w, slot);
-        p[P_ORIGIN] = make_float4(r.o.x, r.o.y, r.o.z, r.tmax);
-        p[P_DIRECTION] = make_float4(r.d.x, r.d.y, r.d.z, __int_as_float(0));
-        p[P_BETA] = make_float4(1.f, 1.f, 1.f, 0.f);
-        p[P_RADIANCE] = make_float4(0.f, 0.f, 0.f, 0.f);
-        p[P_VERTEX_BETA] = make_float4(0.f, 0.f, 0.f, __int_as_float(0)); // w: pending light count
-        p[P_RNG] = pack_rng(smp.state);
+        store_path_ray(p, r.o, r.tmax, r.d, 0);
+        store_path_tail(p, V3(1.f, 1.f, 1.f), KYD_BLACK, smp.state);
     }
     if (blockIdx.x == 0 && threadIdx.x < 16)
         counters->queue[threadIdx.x] = threadIdx.x == Q_RAY0 ? (unsigned long long)wp.nslots : 0ull;
@@ -236,45 +250,65 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
     const int stride = gridDim.x * blockDim.x;
     unsigned rays = 0;
     const int base_i = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int i0 = base_i - (threadIdx.x & 31); i0 < n; i0 += stride)
+    // software pipeline of the gather: the queue entry two iterations ahead and the ray one iteration ahead are
+    // loaded before the current ray is traversed, so their latency hides behind ~1000 instructions of traversal
+    long long ia = base_i;
+    int slot_cur = ia < n ? (IDENTITY ? (int)ia : queue[ia]) : -1;
+    int slot_next = ia + stride < n ? (IDENTITY ? (int)(ia + stride) : queue[ia + stride]) : -1;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
+    if (slot_cur >= 0)
     {
-        const int i = i0 + (threadIdx.x & 31);
-        int lobe = -1, slot = 0;
-        if (i < n)
+        const float4* p0 = path_line(w, slot_cur);
+        o = p0[P_ORIGIN];
+        d = p0[P_DIRECTION];
+    }
+    for (int i0 = base_i - (threadIdx.x & 31); i0 < n; i0 += stride, ia += stride)
+    {
+        int lobe = -1;
+        const int slot = slot_cur < 0 ? 0 : slot_cur;
+        const long long i2 = ia + 2ll * stride;
+        const int slot_next2 = i2 < n ? (IDENTITY ? (int)i2 : queue[i2]) : -1;
+        float4 o_next = make_float4(0.f, 0.f, 0.f, 0.f), d_next = o_next;
+        if (slot_next >= 0)
         {
-            slot = IDENTITY ? i : queue[i];
+            const float4* pn = path_line(w, slot_next);
+            o_next = pn[P_ORIGIN];
+            d_next = pn[P_DIRECTION];
+        }
+        if (slot_cur >= 0)
+        {
             float4* p = path_line(w, slot);
-            float4 o = p[P_ORIGIN], d = p[P_DIRECTION];
             Ray r;
             r.o = V3(o.x, o.y, o.z);
             r.d = V3(d.x, d.y, d.z);
-            r.tmax = o.w;
+            r.tmax = KYD_INF; // extension rays are unbounded (ky.cpp:585, 665-668)
+            const int flags = __float_as_int(d.w);
             float t;
             const int s = scene_closest(r, &t);
             rays++;
             if (s >= 0)
             {
-                p[P_HIT] = make_float4(t, __int_as_float(s), 0.f, 0.f);
-                p[P_HIT_PAD] = make_float4(0.f, 0.f, 0.f, 0.f);
+                // sector 0 goes back whole, now carrying the hit
+                store_path_ray(p, r.o, t, r.d, (flags & (FLAG_PREV_SPECULAR | FLAG_PENDING_MASK)) | ((s + 1) << FLAG_SURFACE_SHIFT));
                 lobe = classify_lobe(s, r, t);
             }
-            else if (has_env && (bounce == 0 || (__float_as_int(d.w) & FLAG_PREV_SPECULAR)))
+            else if (has_env && (bounce == 0 || (flags & FLAG_PREV_SPECULAR)))
             {
                 // Lo += beta * environment_lighting at the camera vertex or after a specular bounce
-                float4 b4 = p[P_BETA], L4 = p[P_RADIANCE], vb = p[P_VERTEX_BETA];
-                float3 Lo = add_pending(w, wp.plane, slot, vb, V3(L4.x, L4.y, L4.z));
-                Lo = add(Lo, cmulc(V3(b4.x, b4.y, b4.z), environment_lighting()));
-                p[P_BETA] = b4;
-                p[P_RADIANCE] = make_float4(Lo.x, Lo.y, Lo.z, 0.f);
-                if (__float_as_int(vb.w) > 0)
-                {
-                    p[P_VERTEX_BETA] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-                    p[P_RNG] = p[P_RNG];
-                }
+                PathState st;
+                unpack_path(st, o, d, p[P_BETA], p[P_TAIL]);
+                float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
+                Lo = add(Lo, cmulc(st.beta, environment_lighting()));
+                store_path_ray(p, r.o, o.w, r.d, flags & FLAG_PREV_SPECULAR); // pending consumed
+                store_path_tail(p, st.beta, Lo, st.rng);
             }
         }
         push.commit(lobe_queues);                                  // the previous iteration's entries
-        push.reserve(lobe >= 0 ? (1u << lobe) : 0u, slot, tails);  // this iteration's atomics, consumed next time round
+        push.reserve(lobe >= 0 ? (1u << lobe) : 0u, slot, tails);  // this iteration's atomic, consumed next time round
+        slot_cur = slot_next;
+        slot_next = slot_next2;
+        o = o_next;
+        d = d_next;
     }
     push.commit(lobe_queues);
     flush_counters(rays, rays, counters);
@@ -290,74 +324,75 @@ KYD_DEV int light_draw_offset(int l, int direct_sample)
     return n;
 }
 
-KYD_DEV void store_nee(float4* line, int first_unit, const NeeRay& q)
-{
-    // tmax < 0 marks "no query"; w of the direction: bit 0 = the reference issues this query (ray statistics)
-    line[first_unit] = make_float4(q.ray.o.x, q.ray.o.y, q.ray.o.z, q.active ? q.ray.tmax : -1.f);
-    line[first_unit + 1] = make_float4(q.ray.d.x, q.ray.d.y, q.ray.d.z, __int_as_float(q.ref_query ? 1 : 0));
-    line[first_unit + 2] = make_float4(q.value.x, q.value.y, q.value.z, 0.f);
-}
-
-// NEE + MIS set-up of one (vertex, light): the two draws, the first halves of the estimators
-// (ky.cpp:3864-3869, 3889-4074), and the queries written to the pair's line
-KYD_DEV void light_sample_pair(const WaveParams& wp, const WaveBuffers& w, const HitGeom& g, const Bsdf& b, int l, int slot, Sampler smp)
+// NEE + MIS set-up of one (vertex, light): the two draws and the first halves of the estimators
+// (ky.cpp:3864-3869, 3889-4074)
+KYD_DEV void light_sample_pair(const WaveParams& wp, const HitGeom& g, const Bsdf& b, int l, Sampler smp, NeeRay* qb, NeeRay* ql)
 {
     const int ds = wp.rp.direct_sample;
     float2 random_bsdf = smp.get_float2();
     float2 random_light = smp.get_float2();
 
-    NeeRay qb, ql;
-    qb.active = ql.active = false;
-    qb.ref_query = ql.ref_query = false;
-    qb.value = ql.value = KYD_BLACK;
-    qb.ray.o = qb.ray.d = ql.ray.o = ql.ray.d = V3(0, 0, 0);
-    qb.ray.tmax = ql.ray.tmax = -1.f;
+    qb->active = ql->active = false;
+    qb->ref_query = ql->ref_query = false;
+    qb->value = ql->value = KYD_BLACK;
+    qb->ray.o = qb->ray.d = ql->ray.o = ql->ray.d = V3(0, 0, 0);
+    qb->ray.tmax = ql->ray.tmax = -1.f;
+    qb->light = ql->light = l;
     if (ds == KYD_DS_BSDF)
     {
         if (!light_is_delta(c_scene.lights[l].kind))
-            qb = nee_bsdf_setup(g, b, l, smp.get_float2(), false);
+            *qb = nee_bsdf_setup(g, b, l, smp.get_float2(), false);
     }
     else if (ds == KYD_DS_BSDF_MIS || ds == KYD_DS_BOTH_MIS)
-        qb = nee_bsdf_setup(g, b, l, random_bsdf, true);
+        *qb = nee_bsdf_setup(g, b, l, random_bsdf, true);
     if (ds == KYD_DS_LIGHT)
-        ql = nee_light_setup(g, b, l, random_light, false);
+        *ql = nee_light_setup(g, b, l, random_light, false);
     else if (ds == KYD_DS_LIGHT_MIS || ds == KYD_DS_BOTH_MIS)
-        ql = nee_light_setup(g, b, l, random_light, true);
+        *ql = nee_light_setup(g, b, l, random_light, true);
+}
 
-    float4* line = nee_line(w, wp.plane, l, slot);
-    store_nee(line, N_BSDF_O, qb);
-    store_nee(line, N_LIGHT_O, ql);
+// writes the light-sampling line of (light, path): sectors 0-1 always, sector 2 only for a live BSDF-sampled query
+KYD_DEV void store_nee_line(float4* line, const NeeRay& qb, const NeeRay& ql, float3 vertex_beta)
+{
+    const int flags = (qb.ref_query ? NEE_REF_BSDF : 0) | (ql.ref_query ? NEE_REF_LIGHT : 0) | (qb.active ? NEE_BSDF_LIVE : 0);
+    line[N_LIGHT_O] = make_float4(ql.ray.o.x, ql.ray.o.y, ql.ray.o.z, ql.active ? ql.ray.tmax : -1.f); // tmax < 0: no query
+    line[N_LIGHT_D] = make_float4(ql.ray.d.x, ql.ray.d.y, ql.ray.d.z, __int_as_float(flags));
+    line[N_LIGHT_VALUE] = make_float4(ql.value.x, ql.value.y, ql.value.z, vertex_beta.x);
+    line[N_MIXED] = make_float4(vertex_beta.y, vertex_beta.z, qb.value.x, qb.value.y);
+    if (qb.active)
+    {
+        line[N_BSDF_O] = make_float4(qb.ray.o.x, qb.ray.o.y, qb.ray.o.z, qb.ray.tmax);
+        line[N_BSDF_D] = make_float4(qb.ray.d.x, qb.ray.d.y, qb.ray.d.z, qb.value.z);
+    }
 }
 
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
-// pre / PRE_STRIDE: where the path line's units are read from -- the line itself (stride 1) or this thread's
-// column of the shared-memory prefetch buffer; pre_result0: light 0's pending estimator value
-template <int LOBE, int PRE_STRIDE>
-KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, const float4* pre, const float4* pre_result0, int slot, int bounce, int n_lights,
-                          bool* out_alive, bool* out_nee)
+template <int LOBE>
+KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee,
+                          unsigned* ref_rays)
 {
     float4* p = path_line(w, slot);
-    float4 o4 = pre[P_ORIGIN * PRE_STRIDE], d4 = pre[P_DIRECTION * PRE_STRIDE], b4 = pre[P_BETA * PRE_STRIDE], L4 = pre[P_RADIANCE * PRE_STRIDE];
-    float4 vb = pre[P_VERTEX_BETA * PRE_STRIDE], rng4 = pre[P_RNG * PRE_STRIDE], h = pre[P_HIT * PRE_STRIDE], res0 = *pre_result0;
+    PathState st;
+    unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
     Ray r;
-    r.o = V3(o4.x, o4.y, o4.z);
-    r.d = V3(d4.x, d4.y, d4.z);
-    r.tmax = o4.w;
-    float3 beta = V3(b4.x, b4.y, b4.z);
-    const int flags = __float_as_int(d4.w);
-    const int surface = __float_as_int(h.y);
+    r.o = st.o;
+    r.d = st.d;
+    r.tmax = KYD_INF;
+    const float3 beta = st.beta;
+    const int surface = st.surface();
 
     // light gathered at the previous vertex (see file header)
-    float3 Lo = add_pending(w, wp.plane, slot, vb, V3(L4.x, L4.y, L4.z), &res0);
+    float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
     int new_pending = 0;
 
-    HitGeom g = shape_hit_geom(c_scene.surf_shape[surface], r, h.x);
+    HitGeom g = shape_hit_geom(c_scene.surf_shape[surface], r, st.t);
 
-    if (bounce == 0 || (flags & FLAG_PREV_SPECULAR))
+    if (bounce == 0 || (st.flags & FLAG_PREV_SPECULAR))
         Lo = add(Lo, cmulc(beta, surface_emission(surface, g)));
 
-    float3 next_beta = beta;
-    unsigned long long rng_state = unpack_rng(rng4);
+    float3 next_o = st.o, next_d = st.d, next_beta = beta;
+    int next_flags = 0;
+    unsigned long long rng_state = st.rng;
     if (bounce < wp.rp.max_depth + wp.direct_only)
     {
         const DevMaterial& m = c_scene.materials[c_scene.surf_material[surface]];
@@ -388,20 +423,38 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, const floa
                     v[V_NORMAL] = make_float4(g.normal.x, g.normal.y, g.normal.z, b.exponent);
                     v[V_WO] = make_float4(g.wo.x, g.wo.y, g.wo.z, 0.f);
                     v[V_COLOR] = make_float4(b.a.x, b.a.y, b.a.z, 0.f);
-                    v[V_RNG] = pack_rng(smp.state);
-                    v[V_PAD] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[V_RNG] = make_float4(__uint_as_float((unsigned)smp.state), __uint_as_float((unsigned)(smp.state >> 32)), 0.f, 0.f);
+                    v[V_BETA] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                    new_pending = n_lights;
+                }
+                else if (n_lights == 1)
+                {
+                    // the common case keeps both queries in registers and writes nothing when neither can contribute
+                    NeeRay qb, ql;
+                    light_sample_pair(wp, g, b, 0, smp, &qb, &ql);
+                    *ref_rays += (qb.ref_query ? 1u : 0u) + (ql.ref_query ? 1u : 0u);
+                    // (beta * 0 is 0 only for finite beta: a non-finite throughput keeps the reference's NaN)
+                    const bool finite_beta = isfinite(beta.x) && isfinite(beta.y) && isfinite(beta.z);
+                    if (qb.active || ql.active || !finite_beta)
+                    {
+                        qb.ref_query = ql.ref_query = false; // counted here
+                        store_nee_line(nee_line(w, wp.plane, 0, slot), qb, ql, beta);
+                        new_pending = 1;
+                    }
                 }
                 else
                 {
                     Sampler ls = smp;
                     for (int l = 0; l < n_lights; ++l)
                     {
-                        light_sample_pair(wp, w, g, b, l, slot, ls);
+                        NeeRay qb, ql;
+                        light_sample_pair(wp, g, b, l, ls, &qb, &ql);
+                        store_nee_line(nee_line(w, wp.plane, l, slot), qb, ql, beta);
                         ls.skip(4 + ((wp.rp.direct_sample == KYD_DS_BSDF && !light_is_delta(c_scene.lights[l].kind)) ? 2 : 0));
                     }
+                    new_pending = n_lights;
                 }
-                new_pending = n_lights;
-                *out_nee = true;
+                *out_nee = new_pending > 0;
             }
             // sample_all_light draws 4 floats per light, plus 2 per non-delta light in `bsdf` mode
             smp.skip(4 * n_lights + (wp.rp.direct_sample == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
@@ -425,8 +478,9 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, const floa
                 }
                 if (alive)
                 {
-                    o4 = make_float4(nr.o.x, nr.o.y, nr.o.z, nr.tmax);
-                    d4 = make_float4(nr.d.x, nr.d.y, nr.d.z, __int_as_float((bs.type & BSDF_SPECULAR) ? FLAG_PREV_SPECULAR : 0));
+                    next_o = nr.o;
+                    next_d = nr.d;
+                    next_flags = (bs.type & BSDF_SPECULAR) ? FLAG_PREV_SPECULAR : 0;
                     next_beta = nb;
                     rng_state = smp.state;
                     *out_alive = true;
@@ -434,23 +488,9 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, const floa
             }
         }
     }
-    // whole sectors go back: the ray, (beta, Lo), (beta of this vertex for its pending Ld, rng)
-    p[P_ORIGIN] = o4;
-    p[P_DIRECTION] = d4;
-    p[P_BETA] = make_float4(next_beta.x, next_beta.y, next_beta.z, 0.f);
-    p[P_RADIANCE] = make_float4(Lo.x, Lo.y, Lo.z, 0.f);
-    p[P_VERTEX_BETA] = make_float4(beta.x, beta.y, beta.z, __int_as_float(new_pending));
-    p[P_RNG] = pack_rng(rng_state);
-}
-
-// gathers one path line (units 0..6) and light 0's pending result into this thread's prefetch column
-KYD_DEV void prefetch_path(const WaveParams& wp, const WaveBuffers& w, float4* column, int slot)
-{
-    const float4* p = path_line(w, slot);
-#pragma unroll
-    for (int k = 0; k < 7; ++k)
-        cp_async16(column + k * SHADE_THREADS, p + k);
-    cp_async16(column + 7 * SHADE_THREADS, nee_line(w, wp.plane, 0, slot) + N_RESULT);
+    // both sectors go back whole
+    store_path_ray(p, next_o, KYD_INF, next_d, next_flags | (new_pending << FLAG_PENDING_SHIFT));
+    store_path_tail(p, next_beta, Lo, rng_state);
 }
 
 template <int LOBE>
@@ -462,63 +502,31 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     int* __restrict__ next_queue = parity ? w.queue_a : w.queue_b;
     const int stride = gridDim.x * blockDim.x;
     const int n_lights = c_scene.n_lights;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     // queue 0: the next bounce's rays; queue 1: vertices whose light queries the shadow stage resolves
     unsigned long long* const tails[2] = { &counters->queue[Q_RAY0 + (parity ^ 1)], &counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)] };
     int* const out_queues[2] = { next_queue, w.queue_nee[LOBE == LOBE_PHONG] };
     WarpPush<2> push;
     push.init();
+    unsigned ref_rays = 0;
 
-#if !defined(KYD_PREFETCH) || !KYD_PREFETCH
-    // default: the line is copied synchronously (KYD_PREFETCH=1 selects the cp.async double-buffered gather
-    // below, which measured 6 % slower: profiles/r01_ab_variants.txt)
-    for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, i += stride)
+    // whole warps iterate together so that the ballots of the push are convergent; the queue entry is read one
+    // iteration ahead
+    long long ia = i;
+    int slot_cur = ia < n ? queue[ia] : -1;
+    for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, ia += stride)
     {
-        bool alive = false, wants_nee = false;
-        int slot = 0;
-        if (i < n)
-        {
-            slot = queue[i];
-            shade_vertex<LOBE, 1>(wp, w, path_line(w, slot), nee_line(w, wp.plane, 0, slot) + N_RESULT, slot, bounce, n_lights, &alive, &wants_nee);
-        }
-        push.commit(out_queues);
-        push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
-    }
-    push.commit(out_queues);
-    return;
-#else
-    // [buffer][unit][thread]: consecutive threads touch consecutive 16-byte words (no bank conflicts); a
-    // thread only ever reads the column it filled itself, so cp.async.wait_group is all the ordering needed
-    __shared__ float4 s_pre[2][8][SHADE_THREADS];
-    int slot_cur = i < n ? queue[i] : -1;
-    int slot_next = (i + stride < n && i + stride >= 0) ? queue[i + stride] : -1;
-    if (slot_cur >= 0)
-        prefetch_path(wp, w, &s_pre[0][0][threadIdx.x], slot_cur);
-    cp_async_commit();
-
-    // whole warps iterate together so that the ballots in queue_push are convergent
-    int buf = 0;
-    for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, i += stride, buf ^= 1)
-    {
-        if (slot_next >= 0)
-            prefetch_path(wp, w, &s_pre[buf ^ 1][0][threadIdx.x], slot_next);
-        cp_async_commit();
-        const long long i2 = (long long)i + 2ll * stride;
-        const int slot_next2 = i2 < n ? queue[i2] : -1;
-        cp_async_wait<1>(); // everything but the newest group has landed: this iteration's line is in shared memory
-
+        const int slot_next = ia + stride < n ? queue[ia + stride] : -1;
         bool alive = false, wants_nee = false;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         if (slot_cur >= 0)
-            shade_vertex<LOBE, SHADE_THREADS>(wp, w, &s_pre[buf][0][threadIdx.x], &s_pre[buf][7][threadIdx.x], slot, bounce, n_lights, &alive, &wants_nee);
+            shade_vertex<LOBE>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &ref_rays);
         push.commit(out_queues);
         push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
         slot_cur = slot_next;
-        slot_next = slot_next2;
     }
     push.commit(out_queues);
-    cp_async_wait<0>();
-#endif
+    flush_counters(ref_rays, 0u, counters);
 }
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
@@ -543,7 +551,7 @@ KYD_DEV void light_sample_queue(const WaveParams& wp, const WaveBuffers& w, DevC
         const int l = (int)(idx / n);            // light-major: a warp works on one light
         const int slot = nee_queue[idx - (long long)l * n];
         const float4* v = vertex_line(w, slot);
-        float4 p4 = v[V_POSITION], n4 = v[V_NORMAL], wo4 = v[V_WO], c4 = v[V_COLOR], rng4 = v[V_RNG];
+        float4 p4 = v[V_POSITION], n4 = v[V_NORMAL], wo4 = v[V_WO], c4 = v[V_COLOR], rng4 = v[V_RNG], vb = v[V_BETA];
         HitGeom g;
         g.position = V3(p4.x, p4.y, p4.z);
         g.normal = V3(n4.x, n4.y, n4.z);
@@ -558,9 +566,11 @@ KYD_DEV void light_sample_queue(const WaveParams& wp, const WaveBuffers& w, DevC
 
         Sampler smp;
         smp.debug = (wp.rp.sampler == KYD_SAMPLER_DEBUG);
-        smp.state = unpack_rng(rng4);
+        smp.state = (unsigned long long)__float_as_uint(rng4.x) | ((unsigned long long)__float_as_uint(rng4.y) << 32);
         smp.skip(light_draw_offset(l, wp.rp.direct_sample));
-        light_sample_pair(wp, w, g, b, l, slot, smp);
+        NeeRay qb, ql;
+        light_sample_pair(wp, g, b, l, smp, &qb, &ql);
+        store_nee_line(nee_line(w, wp.plane, l, slot), qb, ql, V3(vb.x, vb.y, vb.z));
     }
 }
 
@@ -589,37 +599,33 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
             const int l = (int)(idx / n);
             const int slot = nee_queue[idx - (long long)l * n];
             float4* line = nee_line(w, wp.plane, l, slot);
+            const float4 lo = line[N_LIGHT_O], ld = line[N_LIGHT_D], lv = line[N_LIGHT_VALUE], mx = line[N_MIXED];
+            const int flags = __float_as_int(ld.w);
+            rays += (unsigned)((flags & NEE_REF_BSDF) != 0) + (unsigned)((flags & NEE_REF_LIGHT) != 0);
 
             float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
+            if (flags & NEE_BSDF_LIVE)
             {
-                float4 o = line[N_BSDF_O], d = line[N_BSDF_D], v = line[N_BSDF_VALUE];
-                rays += (unsigned)(__float_as_int(d.w) & 1);
-                if (o.w >= 0.f)
-                {
-                    NeeRay q;
-                    q.ray.o = V3(o.x, o.y, o.z);
-                    q.ray.d = V3(d.x, d.y, d.z);
-                    q.ray.tmax = o.w;
-                    q.value = V3(v.x, v.y, v.z);
-                    q.light = l;
-                    float t;
-                    int s = scene_closest(q.ray, &t);
-                    Lb = nee_bsdf_resolve(q, s, t);
-                    traced++;
-                }
+                const float4 bo = line[N_BSDF_O], bd = line[N_BSDF_D];
+                NeeRay q;
+                q.ray.o = V3(bo.x, bo.y, bo.z);
+                q.ray.d = V3(bd.x, bd.y, bd.z);
+                q.ray.tmax = bo.w;
+                q.value = V3(mx.z, mx.w, bd.w);
+                q.light = l;
+                float t;
+                int s = scene_closest(q.ray, &t);
+                Lb = nee_bsdf_resolve(q, s, t);
+                traced++;
             }
+            if (lo.w >= 0.f)
             {
-                float4 o = line[N_LIGHT_O], d = line[N_LIGHT_D], v = line[N_LIGHT_VALUE];
-                rays += (unsigned)(__float_as_int(d.w) & 1);
-                if (o.w >= 0.f)
-                {
-                    Ray r;
-                    r.o = V3(o.x, o.y, o.z);
-                    r.d = V3(d.x, d.y, d.z);
-                    r.tmax = o.w;
-                    Ll = scene_any_hit(r) ? KYD_BLACK : V3(v.x, v.y, v.z);
-                    traced++;
-                }
+                Ray r;
+                r.o = V3(lo.x, lo.y, lo.z);
+                r.d = V3(ld.x, ld.y, ld.z);
+                r.tmax = lo.w;
+                Ll = scene_any_hit(r) ? KYD_BLACK : V3(lv.x, lv.y, lv.z);
+                traced++;
             }
             float3 e;
             if (ds == KYD_DS_BOTH_MIS)
@@ -629,7 +635,7 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
             else
                 e = Ll;
             line[N_RESULT] = make_float4(e.x, e.y, e.z, 0.f);
-            line[N_RESULT_PAD] = make_float4(0.f, 0.f, 0.f, 0.f);
+            line[N_VERTEX_BETA] = make_float4(lv.w, mx.x, mx.y, 0.f);
         }
     }
     flush_counters(rays, traced, counters);
@@ -647,8 +653,9 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveParams wp, WaveBuffers w
         {
             const int slot = s * wp.npix + px;
             const float4* p = path_line(w, slot);
-            float4 L4 = p[P_RADIANCE];
-            float3 Li = add_pending(w, wp.plane, slot, p[P_VERTEX_BETA], V3(L4.x, L4.y, L4.z));
+            PathState st;
+            unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
+            float3 Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
             L = add(L, mul(Li, wp.rp.weight));
         }
         o[0] = L.x; o[1] = L.y; o[2] = L.z;
