@@ -159,9 +159,12 @@ class Scene:
         self.width, self.height = width, height
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            host().ky_host_scene_destroy(self._h)
-            self._h = None
+        try:
+            if getattr(self, "_h", None):
+                host().ky_host_scene_destroy(self._h)
+                self._h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @property
     def shapes(self):
@@ -229,7 +232,10 @@ class Device:
             self._ctx = None
 
     def __del__(self):
-        self.close()
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
     def _check(self, rc):
         if rc != 0:
