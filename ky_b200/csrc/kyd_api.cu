@@ -396,12 +396,13 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out)
 int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2)
 {
     if (!ctx || !out2) return KYD_ERR_INVALID;
-    if (which != KYD_SELFTEST_RSQRT) return fail(ctx, KYD_ERR_INVALID, "unknown self-test");
+    if (which != KYD_SELFTEST_RSQRT && which != KYD_SELFTEST_POW) return fail(ctx, KYD_ERR_INVALID, "unknown self-test");
     KYD_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned long long* dev = nullptr;
     KYD_CUDA(ctx, cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
     cudaMemsetAsync(dev, 0, 2 * sizeof(unsigned long long), ctx->stream);
-    launch_selftest_rsqrt(first, count, dev, ctx->stream);
+    if (which == KYD_SELFTEST_RSQRT) launch_selftest_rsqrt(first, count, dev, ctx->stream);
+    else launch_selftest_pow(first, count, dev, ctx->stream);
     unsigned long long host[2] = { 0, 0 };
     cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -60,7 +60,39 @@ KYD_MATH void cr_sincos(float x, float* s, float* c)
     *c = __double2float_rn(dc);
 }
 KYD_MATH float cr_acos(float x) { return __double2float_rn(acos((double)x)); }
-KYD_MATH float cr_pow(float x, float y) { return __double2float_rn(pow((double)x, (double)y)); }
+// powf's contract value: the double pow rounded once (the definition; slow path of cr_pow)
+KYD_MATH float cr_pow_reference(float x, float y) { return __double2float_rn(pow((double)x, (double)y)); }
+
+// The same float for the cases Phong shading produces (x > 0), at a third of the cost: v = exp2(y * log2(x)) in
+// double is within 2^-45 of x^y when |y log2 x| < 120 (log2 and exp2 are 1-ulp functions; the product's error is
+// 2^-52 |y log2 x|), the definition's double pow is within 2^-52 of it; if v sits at least 2^-41 (relative) inside
+// its float rounding interval both round to the same float.  Results below 2^-160 round to +0 either way.
+// Everything else -- x <= 0, non-finite or huge arguments, denormal results, values too close to a rounding
+// boundary (2^-15 of calls) -- evaluates the definition.  tests: kyd_selftest(KYD_SELFTEST_POW).
+KYD_DEV float cr_pow(float x, float y)
+{
+#if !defined(KYD_FAST_POW) || KYD_FAST_POW
+    if (x > 0x1p-100f && x < 0x1p100f && fabsf(y) < 1e6f)
+    {
+        const double t = (double)y * log2((double)x);
+        if (t < -160.0)
+            return 0.f;
+        if (fabs(t) < 120.0)
+        {
+            const double v = exp2(t);
+            const float f = __double2float_rn(v);
+            const double d = v - (double)f;
+            const unsigned fb = __float_as_uint(f);
+            const double half_ulp = (double)__uint_as_float((fb & 0x7f800000u) - (24u << 23));
+            const double hi = half_ulp * (1.0 - 0x1p-16);
+            const double lo = (fb & 0x007fffffu) != 0u ? -hi : -0.5 * hi;
+            if (d < hi && d > lo)
+                return f;
+        }
+    }
+#endif
+    return cr_pow_reference(x, y);
+}
 
 // ---- vectors (ky.cpp:226-388) -----------------------------------------------------------------------
 KYD_DEV float3 V3(float x, float y, float z) { return make_float3(x, y, z); }
@@ -249,6 +281,20 @@ KYD_DEV float plastic_random(float3 p, float3 wo)
     return (float)(unsigned)(h >> 40) * 0x1p-24f;
 }
 
+#ifndef KYD_TRAITS
+#define KYD_TRAITS 0
+#endif
+#if KYD_TRAITS == 1
+#define KYD_LIGHT_KIND(l) KYD_LIGHT_AREA
+#define KYD_LIGHT_SHAPE_KIND(s) KYD_SHAPE_RECTANGLE
+#elif KYD_TRAITS == 2
+#define KYD_LIGHT_KIND(l) KYD_LIGHT_AREA
+#define KYD_LIGHT_SHAPE_KIND(s) KYD_SHAPE_SPHERE
+#else
+#define KYD_LIGHT_KIND(l) ((l).kind)
+#define KYD_LIGHT_SHAPE_KIND(s) ((s).kind)
+#endif
+
 // ---- shapes ky.cpp:1009-1519 ------------------------------------------------------------------------------
 struct Ray { float3 o, d; float tmax; };
 struct HitGeom { float3 position, normal, wo; };
@@ -346,7 +392,7 @@ KYD_DEV HitGeom shape_hit_geom(const DevShape& s, const Ray& r, float t)
 // shape_t::sample_position ky.cpp:1144, 1225, 1307, 1404
 KYD_DEV void shape_sample_position(const DevShape& s, float2 u, float3* lp, float3* ln, float* area_pdf)
 {
-    switch (s.kind)
+    switch (KYD_LIGHT_SHAPE_KIND(s))
     {
     case KYD_SHAPE_SPHERE:
     {
@@ -382,7 +428,7 @@ KYD_DEV void shape_sample_position(const DevShape& s, float2 u, float3* lp, floa
 // shape_t::sample_direction ky.cpp:1028-1051 and sphere_t's override ky.cpp:1419-1501
 KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade, float2 u, float3* lp, float3* ln, float* pdf)
 {
-    if (s.kind == KYD_SHAPE_SPHERE)
+    if (KYD_LIGHT_SHAPE_KIND(s) == KYD_SHAPE_SPHERE)
     {
         float3 center = s.p0;
         float radius = s.radius;
@@ -452,7 +498,7 @@ KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade,
 // shape_t::pdf_direction ky.cpp:1055-1090 and sphere_t's override ky.cpp:1503-1513
 KYD_DEV float shape_pdf_direction(const DevShape& s, float3 p, float3 n_shade, float3 wi)
 {
-    if (s.kind == KYD_SHAPE_SPHERE)
+    if (KYD_LIGHT_SHAPE_KIND(s) == KYD_SHAPE_SPHERE)
     {
         if (!(distance_sq(p, s.p0) <= s.radius * s.radius))
         {
@@ -563,10 +609,24 @@ KYD_DEV float bsdf_pdf_local(const Bsdf& b, float3 wo, float3 wi) // ky.cpp:2237
     return 0;
 }
 
-// phong eval_ and pdf_ of the same (wo, wi) share one pow(): both raise to the same exponent and
-// max(0, c) differs from c only where pow's result is unused or c < 0
+// eval_ and pdf_ of the same (wo, wi).  Phong raises cos_alpha (eval_, ky.cpp:2499) and max(0, cos_alpha)
+// (pdf_, ky.cpp:2548) to the same exponent: for cos_alpha > 0 that is one pow() instead of two -- the same
+// value by definition; every other case (zero, negative, NaN) takes the two separate calls.
 KYD_DEV void bsdf_eval_pdf_local(const Bsdf& b, float3 wo, float3 wi, float3* f, float* pdf)
 {
+    if (b.lobe == LOBE_PHONG)
+    {
+        float3 wr = reflect_z(wo);
+        float cos_alpha = dot(wr, wi);
+        if (cos_alpha > 0.f)
+        {
+            const float pw = cr_pow(cos_alpha, b.exponent);
+            float3 rho = mul(mul(b.a, b.exponent + 2.f), KYD_INV_2PI);
+            *f = same_hemisphere(wo, wi) ? mul(rho, pw) : KYD_BLACK;
+            *pdf = (b.exponent + 1.f) * pw * KYD_INV_2PI;
+            return;
+        }
+    }
     *f = bsdf_eval_local(b, wo, wi);
     *pdf = bsdf_pdf_local(b, wo, wi);
 }
@@ -643,8 +703,7 @@ KYD_DEV BsdfSample bsdf_sample(const Bsdf& b, float3 world_wo, float2 u)
         s.wi = to_world(fr, local);
         if (wo.z < 0)
             s.wi.z *= -1;
-        s.f = bsdf_eval_local(b, wo, s.wi);
-        s.pdf = bsdf_pdf_local(b, wo, s.wi);
+        bsdf_eval_pdf_local(b, wo, s.wi, &s.f, &s.pdf);
         s.type = BSDF_REFLECTION | BSDF_GLOSSY;
     }
 
@@ -777,21 +836,21 @@ KYD_DEV LightSample light_sample_Li(int light_index, const HitGeom& g, float2 u)
     s.wi = V3(0, 0, 0);
     s.pdf = 0;
     s.Li = KYD_BLACK;
-    if (l.kind == KYD_LIGHT_POINT) // ky.cpp:2825-2853
+    if (KYD_LIGHT_KIND(l) == KYD_LIGHT_POINT) // ky.cpp:2825-2853
     {
         s.position = l.position;
         s.wi = normalize(sub(l.position, g.position));
         s.pdf = 1.f;
         s.Li = cdiv(l.color, distance_sq(l.position, g.position));
     }
-    else if (l.kind == KYD_LIGHT_DIRECTION) // ky.cpp:2891-2901
+    else if (KYD_LIGHT_KIND(l) == KYD_LIGHT_DIRECTION) // ky.cpp:2891-2901
     {
         s.wi = neg(l.direction);
         s.position = add(g.position, mul(mul(s.wi, 2.f), l.world_radius));
         s.pdf = 1;
         s.Li = l.color;
     }
-    else if (l.kind == KYD_LIGHT_AREA) // ky.cpp:2964-2981
+    else if (KYD_LIGHT_KIND(l) == KYD_LIGHT_AREA) // ky.cpp:2964-2981
     {
         float3 lp, ln;
         shape_sample_direction(c_scene.light_shape[light_index], g.position, g.normal, u, &lp, &ln, &s.pdf);
@@ -818,9 +877,9 @@ KYD_DEV LightSample light_sample_Li(int light_index, const HitGeom& g, float2 u)
 KYD_DEV float light_pdf_Li(int light_index, const HitGeom& g, float3 wi)
 {
     const DevLight& l = c_scene.lights[light_index];
-    if (l.kind == KYD_LIGHT_AREA) // ky.cpp:2984-2988
+    if (KYD_LIGHT_KIND(l) == KYD_LIGHT_AREA) // ky.cpp:2984-2988
         return shape_pdf_direction(c_scene.light_shape[light_index], g.position, g.normal, wi);
-    if (l.kind == KYD_LIGHT_ENVIRONMENT) // ky.cpp:3043-3053
+    if (KYD_LIGHT_KIND(l) == KYD_LIGHT_ENVIRONMENT) // ky.cpp:3043-3053
     {
         float sin_theta = cr_sin(spherical_theta(wi));
         if (sin_theta == 0)
@@ -855,7 +914,7 @@ KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, 
     q.light = light_index;
     q.value = KYD_BLACK;
     const DevLight& l = c_scene.lights[light_index];
-    if (bsdf_is_delta(b.lobe) || light_is_delta(l.kind))
+    if (bsdf_is_delta(b.lobe) || light_is_delta(KYD_LIGHT_KIND(l)))
         return q;
     BsdfSample bs = bsdf_sample(b, g.wo, random_bsdf);
     float3 f_cos = mul(bs.f, abs_dot(bs.wi, g.normal));
@@ -913,14 +972,23 @@ KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index,
     q.ref_query = true;
     q.ray = shadow_ray(g, ls.position);
     float3 wo_l = to_local(b.f, g.wo), wi_l = to_local(b.f, ls.wi);
-    float3 f_cos = mul(bsdf_eval_local(b, wo_l, wi_l), abs_dot(ls.wi, g.normal));
+    float3 f_eval;
+    float bsdf_pdf_v;
+    const bool need_pdf = mis && !light_is_delta(KYD_LIGHT_KIND(l));
+    if (need_pdf)
+        bsdf_eval_pdf_local(b, wo_l, wi_l, &f_eval, &bsdf_pdf_v);
+    else
+    {
+        f_eval = bsdf_eval_local(b, wo_l, wi_l);
+        bsdf_pdf_v = 0.f;
+    }
+    float3 f_cos = mul(f_eval, abs_dot(ls.wi, g.normal));
     if (is_black(f_cos))
         return q;
-    if (!mis || light_is_delta(l.kind))
+    if (!need_pdf)
         q.value = cdiv(cmulc(f_cos, ls.Li), ls.pdf);
     else
     {
-        float bsdf_pdf_v = bsdf_pdf_local(b, wo_l, wi_l);
         q.value = cdiv(mul(cmulc(f_cos, ls.Li), 2.f), ls.pdf + bsdf_pdf_v);
     }
     q.active = true;

@@ -56,6 +56,7 @@ void launch_render_pixels(const RenderParams& rp, float* film_dev, DevCounters* 
 
 void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 
+void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 
 void free_wave_buffers(WaveBuffers& w);

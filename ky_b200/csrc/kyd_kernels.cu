@@ -414,6 +414,44 @@ __global__ void k_selftest_rsqrt(unsigned long long first, unsigned long long co
     if (slow) atomicAdd(&out[1], slow);
 }
 
+// pow: (x, y) pairs derived from the index: the exponents Phong shading uses (n and 1/(n+1) for n = 30, 90, 5000),
+// random exponents, bases over (0, 4) with extra density next to 1
+__global__ void k_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* __restrict__ out)
+{
+    unsigned long long bad = 0, slow = 0;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride)
+    {
+        const unsigned long long h = mix64(first + i), h2 = mix64(h ^ 0x9E3779B97F4A7C15ull);
+        const float u = (float)(unsigned)(h >> 40) * 0x1p-24f, v = (float)(unsigned)(h2 >> 40) * 0x1p-24f;
+        const int k = (int)(h & 15);
+        float x, y;
+        const float ys[6] = { 90.f, 5000.f, 30.f, 1.f / 91.f, 1.f / 5001.f, 1.f / 31.f };
+        if (k < 6) { y = ys[k]; x = k < 3 ? 1.f - u * v * 0.05f : u; }
+        else if (k < 12) { y = ys[k - 6]; x = k < 9 ? 1.f - u * u * u : u * v; }
+        else { y = (v * 2.f - 1.f) * 100.f; x = u * 4.f; }
+        const float want = cr_pow_reference(x, y);
+        const float got = cr_pow(x, y);
+        if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got))
+            ++bad;
+        // a second evaluation of the fast path's conditions to count how often the definition was needed
+        bool fast = false;
+        if (x > 0x1p-100f && x < 0x1p100f && fabsf(y) < 1e6f)
+        {
+            const double t = (double)y * log2((double)x);
+            fast = t < -160.0 || fabs(t) < 120.0;
+        }
+        if (!fast) ++slow;
+    }
+    if (bad) atomicAdd(&out[0], bad);
+    if (slow) atomicAdd(&out[1], slow);
+}
+
+void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream)
+{
+    k_selftest_pow<<<148 * 16, 256, 0, stream>>>(first, count, out_dev);
+}
+
 void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream)
 {
     k_selftest_rsqrt<<<148 * 16, 256, 0, stream>>>(first, count, out_dev);

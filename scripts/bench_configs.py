@@ -24,7 +24,7 @@ CONFIGS = [
     ("-- pixel kernel: cornell 1024x768 pt_recursion d5", ky.SCENE_CORNELL, ky.CB_DEFAULT, 1024, 768, ky.INT_PT_RECURSION, 5, ky.DS_BOTH_MIS, -64),
 ]
 for name, sid, flags, w, h, integ, depth, ds, spp in CONFIGS:
-    fl = ky.FLAG_FUSED if spp < 0 else 0
+    fl = ky.FLAG_FUSED if spp < 0 else int(os.environ.get("KYD_BENCH_FLAGS", "0"))
     spp = abs(spp)
     scene = ky.Scene(sid, w, h, flags)
     dev.upload(scene)

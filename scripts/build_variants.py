@@ -3,11 +3,9 @@ import os, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 variants = {
-    "mb4": ["-DKYD_SHADE_MIN_BLOCKS=4"],
-    "mb3": ["-DKYD_SHADE_MIN_BLOCKS=3"],
-    "mb3_inline": ["-DKYD_SHADE_MIN_BLOCKS=3", "-DKYD_MATH_INLINE=1"],
-    "mb4_inline": ["-DKYD_SHADE_MIN_BLOCKS=4", "-DKYD_MATH_INLINE=1"],
-    "mb2_inline": ["-DKYD_SHADE_MIN_BLOCKS=2", "-DKYD_MATH_INLINE=1"],
+    "base": [],
+    "traits1": ["-DKYD_TRAITS=1"],
+    "traits1_inline": ["-DKYD_TRAITS=1", "-DKYD_MATH_INLINE=1"],
 }
 names = sys.argv[1:] or list(variants)
 os.makedirs(os.path.join(g.LIB, "ab"), exist_ok=True)

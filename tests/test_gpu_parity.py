@@ -84,6 +84,14 @@ def test_fast_rsqrt_is_exact_for_every_float(device):
     assert slow - outside < 2e-4 * in_range, (slow, outside)
 
 
+def test_fast_pow_matches_its_definition(device):
+    """powf contract value (float)pow((double)x, (double)y): the exp2/log2 fast path with its rounding-interval check
+    agrees with the definition on 2^31 argument pairs (Phong exponents, random exponents, bases dense near 1)."""
+    bad, slow = device.selftest(1, 12345, 1 << 31)
+    assert bad == 0
+    assert slow < 0.2 * (1 << 31)
+
+
 def test_debug_sampler(device):
     scene = cases.make_scene("cornell")
     desc = ky.render_desc(cases.W, cases.H, 2, sampler=ky.SAMPLER_DEBUG)
