@@ -30,6 +30,15 @@ WIDTH, HEIGHT, JOB_SPP, DEPTH = 3840, 2160, 16384, 5
 # brute-force miss cost per ray query, Cornell default scene = 10 rectangles x 68 + 2 spheres x 16
 FLOP_PER_RAY = 10 * 68 + 2 * 16
 SM_COUNT, LANES_PER_SM = 148, 128
+STAGES = ["raygen", "intersect", "shade", "light_sample", "shadow", "-", "accumulate", "pixel"]
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_shade<Lambert> launch (ncu --set full, profiles/r01_final_kernels.txt)
+NCU_SHADE_TRAFFIC = 1515416576  # bytes, k_shade<Lambert> of bounce 1 of a 16.6 M-path wave
+
+
+def JOB_WAVES(spp_per_step, capacity=1 << 24):
+    """waves one step is cut into by the default wave size"""
+    per_wave = max(1, capacity // (WIDTH * HEIGHT))
+    return -(-spp_per_step // per_wave)
 
 
 def measured_peaks():
@@ -153,6 +162,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # CUDA events around every kernel of the wavefront, on the stream it is launched on: the live per-stage
+    # durations the roofline of the dominant kernel is computed from
+    os.environ["KYD_STAGE_TIMING"] = "1"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -196,6 +208,7 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps + 1)]
     launches = rays = traced = 0
     stage_ms = [0.0] * 8
+    shade = [0, 0]
     for k in range(args.steps):
         flush.zero_()  # L2 flush between timed iterations, outside the per-step events
         ev[k][0].record()
@@ -207,6 +220,8 @@ def main():
         traced += st.rays_traced
         for j in range(8):
             stage_ms[j] += st.stage_ms[j]
+        shade[0] += st.shade_vertices
+        shade[1] += st.shade_light_lines
     # the job's last act: one reduce of the partial films over NVLink, clamp on the root
     ev[-1][0].record()
     if world > 1:
@@ -259,6 +274,22 @@ def main():
         # FP32-issue roofline of the ray-query work; per GPU
         peak_lane_ops = SM_COUNT * LANES_PER_SM * peaks["sm_max_mhz"] * 1e6
         achieved_flops = rays_all * FLOP_PER_RAY / (kernels_ms * 1e-3) / world
+        # dominant kernel = the stage with the largest live duration (rank 0's events)
+        dom = max(range(8), key=lambda j: stage_ms[j])
+        if dom == 2 and shade[0] > 0:
+            # shade: gathers a 64-byte path record per vertex and rewrites it (+4 B queue entry in, +4..8 B out), folds in
+            # pending 32-byte results, writes 64-byte light-sampling lines -- HBM-bound on scattered records
+            alg_bytes = 136 * shade[0] + 64 * shade[1]  # (the 32-byte reads of pending results are left out: a lower bound)
+            launches_dom = 4 * (DEPTH + 1) * (JOB_WAVES(S)) * args.steps
+            roofline = {"bound": "hbm", "kernel": "k_shade<lobe> (4 launches per bounce)", "achieved": alg_bytes / (stage_ms[2] * 1e-3) / 1e9,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / (stage_ms[2] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "traffic": NCU_SHADE_TRAFFIC,
+                        "algorithmic_bytes_per_step": alg_bytes / args.steps, "ms_per_step": stage_ms[2] / args.steps,
+                        "note": f"peak = {peaks['source']} copy bandwidth; the access pattern is a gather/scatter of 64-byte records through lobe-sorted "
+                                "queues, for which tools/membench.cu measures 3.7-3.9 TB/s on this part (profiles/r01_membench.txt)"}
+        else:
+            roofline = {"bound": "fp32_issue", "kernel": STAGES[dom], "achieved": achieved_flops / 1e12, "peak": peak_lane_ops / 1e12,
+                        "unit": "TFLOP/s (FP32 lane-ops/s, FMA off)", "frac": achieved_flops / peak_lane_ops, "traffic": None}
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,17 +302,16 @@ def main():
             "mrays_traced_per_s": traced_all / (total_ms * 1e-3) / 1e6,
             "rays_per_sample": rays_all / samples,
             "reduce_ms": reduce_ms,
-            "stage_ms_per_step": ({n: stage_ms[j] / args.steps for j, n in enumerate(["raygen", "intersect", "shade", "light_sample", "shadow", "-", "accumulate", "pixel"]) if stage_ms[j] > 0}
-                                  if os.environ.get("KYD_STAGE_TIMING") == "1" else None),
+            "stage_ms_per_step": {n: stage_ms[j] / args.steps for j, n in enumerate(STAGES) if stage_ms[j] > 0},
             "gpu_launches": int(launches_all),
             "clocks": clock_info,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": scene_bytes, "d2h_bytes_per_step": WIDTH * HEIGHT * 3 * 4,
                     "steps": e2e_steps},
-            "roofline": {"bound": "fp32_issue", "achieved": achieved_flops / 1e12, "peak": peak_lane_ops / 1e12, "unit": "TFLOP/s (FP32 lane-ops/s, FMA off)",
-                         "frac": achieved_flops / peak_lane_ops, "traffic": None,
-                         "note": f"algorithmic ray-query work = {FLOP_PER_RAY} flop/ray x reference-equivalent rays, per GPU; peak = {SM_COUNT} SMs x {LANES_PER_SM} lanes x "
-                                 f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} max SM clock; median under load {sm_mhz}); tensor cores unused (no contraction)",
-                         "hbm_peak_gbs": peaks["hbm_gbs"]},
+            "roofline": roofline,
+            "roofline_fp32_issue": {"achieved": achieved_flops / 1e12, "peak": peak_lane_ops / 1e12, "unit": "TFLOP/s (FP32 lane-ops/s, FMA off)",
+                                    "frac": achieved_flops / peak_lane_ops,
+                                    "note": f"whole step: {FLOP_PER_RAY} flop/ray x reference-equivalent rays, per GPU; peak = {SM_COUNT} SMs x {LANES_PER_SM} lanes x "
+                                            f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} max SM clock; median under load {sm_mhz}); tensor cores unused"},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference()

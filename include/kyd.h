@@ -181,7 +181,10 @@ typedef struct kyd_stats
     uint64_t rays_traced;       /* scene queries the device actually traversed (it skips those that cannot change the result) */
     uint64_t kernel_launches;   /* kernels launched by the last call */
     double device_ms;           /* CUDA-event time of the last call's kernels (excludes host copies) */
-    double stage_ms[8];         /* raygen, intersect, shade, light_sample, shadow, scatter, accumulate, fused */
+    double stage_ms[8];         /* raygen, intersect, shade, light_sample, shadow, -, accumulate, per-pixel kernel;
+                                   filled when the context was created with KYD_STAGE_TIMING=1 in the environment */
+    uint64_t shade_vertices;      /* wavefront: path vertices shaded */
+    uint64_t shade_light_lines;   /* wavefront: light-sampling lines written by shade (64 B, 96 B with a live BSDF query) */
 } kyd_stats;
 
 typedef struct kyd_ctx kyd_ctx;

@@ -196,6 +196,8 @@ void finish_stats(kyd_ctx* ctx, bool timed)
 {
     ctx->stats.rays = ctx->counters_pinned->rays;
     ctx->stats.rays_traced = ctx->counters_pinned->rays_traced;
+    ctx->stats.shade_vertices = ctx->counters_pinned->shade_vertices;
+    ctx->stats.shade_light_lines = ctx->counters_pinned->shade_lines;
     if (ctx->stage_timing) ctx->timer.collect(ctx->stats.stage_ms);
     if (timed)
     {

@@ -16,6 +16,7 @@ struct DevCounters
     unsigned long long rays;        // scene queries the reference issues for the same samples
     unsigned long long rays_traced; // scene queries actually traversed on the device
     unsigned long long queue[16];   // wavefront queue tails (layout: kyd_wavefront.cuh)
+    unsigned long long shade_vertices, shade_lines; // wavefront shade: vertices shaded, light-sampling lines written
 };
 
 // wavefront buffers (device memory owned by the context), capacity = paths per wave

@@ -366,10 +366,13 @@ KYD_DEV void store_nee_line(float4* line, const NeeRay& qb, const NeeRay& ql, fl
     }
 }
 
+// what shade did, for the statistics: reference-equivalent scene queries it accounted for
+struct ShadeCounts { unsigned ref_rays; };
+
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
 template <int LOBE>
 KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee,
-                          unsigned* ref_rays)
+                          ShadeCounts* counts)
 {
     float4* p = path_line(w, slot);
     PathState st;
@@ -432,7 +435,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                     // the common case keeps both queries in registers and writes nothing when neither can contribute
                     NeeRay qb, ql;
                     light_sample_pair(wp, g, b, 0, smp, &qb, &ql);
-                    *ref_rays += (qb.ref_query ? 1u : 0u) + (ql.ref_query ? 1u : 0u);
+                    counts->ref_rays += (qb.ref_query ? 1u : 0u) + (ql.ref_query ? 1u : 0u);
                     // (beta * 0 is 0 only for finite beta: a non-finite throughput keeps the reference's NaN)
                     const bool finite_beta = isfinite(beta.x) && isfinite(beta.y) && isfinite(beta.z);
                     if (qb.active || ql.active || !finite_beta)
@@ -508,7 +511,9 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     int* const out_queues[2] = { next_queue, w.queue_nee[LOBE == LOBE_PHONG] };
     WarpPush<2> push;
     push.init();
-    unsigned ref_rays = 0;
+    ShadeCounts counts = { 0u };
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&counters->shade_vertices, (unsigned long long)n); // traffic model of bench.py
 
     // whole warps iterate together so that the ballots of the push are convergent; the queue entry is read one
     // iteration ahead
@@ -520,13 +525,13 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
         bool alive = false, wants_nee = false;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         if (slot_cur >= 0)
-            shade_vertex<LOBE>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &ref_rays);
+            shade_vertex<LOBE>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &counts);
         push.commit(out_queues);
         push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
         slot_cur = slot_next;
     }
     push.commit(out_queues);
-    flush_counters(ref_rays, 0u, counters);
+    flush_counters(counts.ref_rays, 0u, counters);
 }
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
@@ -592,6 +597,8 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
     for (int c = 0; c < 2; ++c)
     {
         const int n = (int)counters->queue[Q_NEE0 + c];
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicAdd(&counters->shade_lines, (unsigned long long)n * n_lights); // lines shade wrote for this stage
         const int* __restrict__ nee_queue = w.queue_nee[c];
         const long long total = (long long)n * n_lights;
         for (long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
