@@ -281,19 +281,16 @@ KYD_DEV float plastic_random(float3 p, float3 wo)
     return (float)(unsigned)(h >> 40) * 0x1p-24f;
 }
 
-#ifndef KYD_TRAITS
-#define KYD_TRAITS 0
-#endif
-#if KYD_TRAITS == 1
-#define KYD_LIGHT_KIND(l) KYD_LIGHT_AREA
-#define KYD_LIGHT_SHAPE_KIND(s) KYD_SHAPE_RECTANGLE
-#elif KYD_TRAITS == 2
-#define KYD_LIGHT_KIND(l) KYD_LIGHT_AREA
-#define KYD_LIGHT_SHAPE_KIND(s) KYD_SHAPE_SPHERE
-#else
-#define KYD_LIGHT_KIND(l) ((l).kind)
-#define KYD_LIGHT_SHAPE_KIND(s) ((s).kind)
-#endif
+// Scene traits: which light kinds / light shapes can occur, known when the scene is uploaded.  Kernels instantiated
+// for a restricted scene drop the code of the other kinds (the shade kernels are instruction-fetch sensitive:
+// profiles/r01_ab_variants.txt).  0 = anything; 1 = area lights on rectangles only (Cornell); 2 = area lights on
+// spheres only (Veach).
+enum { TRAITS_ANY = 0, TRAITS_AREA_RECTANGLE = 1, TRAITS_AREA_SPHERE = 2 };
+template <int TRAITS> KYD_DEV int light_kind(const DevLight& l) { return TRAITS == TRAITS_ANY ? l.kind : KYD_LIGHT_AREA; }
+template <int TRAITS> KYD_DEV int light_shape_kind(const DevShape& s)
+{
+    return TRAITS == TRAITS_AREA_RECTANGLE ? KYD_SHAPE_RECTANGLE : TRAITS == TRAITS_AREA_SPHERE ? KYD_SHAPE_SPHERE : s.kind;
+}
 
 // ---- shapes ky.cpp:1009-1519 ------------------------------------------------------------------------------
 struct Ray { float3 o, d; float tmax; };
@@ -311,9 +308,9 @@ KYD_DEV bool is_equal0(float x) // is_equal(x, 0) ky.cpp:213-220
 // the hit test of shape_t::intersect WITHOUT filling the isect: returns true and the distance when the
 // shape is hit inside (epsilon, tmax).  The isect is a pure function of (ray, distance, shape) and is
 // filled once for the final hit by shape_hit_geom().
-KYD_DEV bool shape_hit_distance(const DevShape& s, const Ray& r, float tmax, float* out_t)
+KYD_DEV bool shape_hit_distance_kind(const DevShape& s, int kind, const Ray& r, float tmax, float* out_t)
 {
-    switch (s.kind)
+    switch (kind)
     {
     case KYD_SHAPE_SPHERE: // ky.cpp:1365-1383
     {
@@ -374,13 +371,18 @@ KYD_DEV bool shape_hit_distance(const DevShape& s, const Ray& r, float tmax, flo
     }
 }
 
+KYD_DEV bool shape_hit_distance(const DevShape& s, const Ray& r, float tmax, float* out_t)
+{
+    return shape_hit_distance_kind(s, s.kind, r, tmax, out_t);
+}
+
 // the isect_t a shape builds for a hit at distance t (ky.cpp:1125, 1208, 1288-1290, 1388-1389)
-KYD_DEV HitGeom shape_hit_geom(const DevShape& s, const Ray& r, float t)
+KYD_DEV HitGeom shape_hit_geom_kind(const DevShape& s, int kind, const Ray& r, float t)
 {
     HitGeom g;
     g.position = ray_at(r, t);
     g.wo = neg(r.d);
-    switch (s.kind)
+    switch (kind)
     {
     case KYD_SHAPE_SPHERE: g.normal = normalize(sub(g.position, s.p0)); break;
     case KYD_SHAPE_RECTANGLE: g.normal = dot(s.n, r.d) <= 0 ? s.n : neg(s.n); break;
@@ -389,10 +391,13 @@ KYD_DEV HitGeom shape_hit_geom(const DevShape& s, const Ray& r, float t)
     return g;
 }
 
+KYD_DEV HitGeom shape_hit_geom(const DevShape& s, const Ray& r, float t) { return shape_hit_geom_kind(s, s.kind, r, t); }
+
 // shape_t::sample_position ky.cpp:1144, 1225, 1307, 1404
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV void shape_sample_position(const DevShape& s, float2 u, float3* lp, float3* ln, float* area_pdf)
 {
-    switch (KYD_LIGHT_SHAPE_KIND(s))
+    switch (light_shape_kind<TRAITS>(s))
     {
     case KYD_SHAPE_SPHERE:
     {
@@ -426,16 +431,17 @@ KYD_DEV void shape_sample_position(const DevShape& s, float2 u, float3* lp, floa
 }
 
 // shape_t::sample_direction ky.cpp:1028-1051 and sphere_t's override ky.cpp:1419-1501
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade, float2 u, float3* lp, float3* ln, float* pdf)
 {
-    if (KYD_LIGHT_SHAPE_KIND(s) == KYD_SHAPE_SPHERE)
+    if (light_shape_kind<TRAITS>(s) == KYD_SHAPE_SPHERE)
     {
         float3 center = s.p0;
         float radius = s.radius;
         if (distance_sq(p, center) <= radius * radius)
         {
             float area_pdf;
-            shape_sample_position(s, u, lp, ln, &area_pdf);
+            shape_sample_position<TRAITS>(s, u, lp, ln, &area_pdf);
             float3 wi = sub(*lp, p);
             if (msq(wi) == 0)
                 *pdf = 0;
@@ -482,7 +488,7 @@ KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade,
     }
 
     float area_pdf;
-    shape_sample_position(s, u, lp, ln, &area_pdf);
+    shape_sample_position<TRAITS>(s, u, lp, ln, &area_pdf);
     float3 wi = sub(*lp, p);
     if (msq(wi) == 0)
         *pdf = 0;
@@ -496,9 +502,10 @@ KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade,
 }
 
 // shape_t::pdf_direction ky.cpp:1055-1090 and sphere_t's override ky.cpp:1503-1513
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV float shape_pdf_direction(const DevShape& s, float3 p, float3 n_shade, float3 wi)
 {
-    if (KYD_LIGHT_SHAPE_KIND(s) == KYD_SHAPE_SPHERE)
+    if (light_shape_kind<TRAITS>(s) == KYD_SHAPE_SPHERE)
     {
         if (!(distance_sq(p, s.p0) <= s.radius * s.radius))
         {
@@ -512,9 +519,9 @@ KYD_DEV float shape_pdf_direction(const DevShape& s, float3 p, float3 n_shade, f
     r.d = wi;
     r.tmax = KYD_INF;
     float t;
-    if (!shape_hit_distance(s, r, r.tmax, &t))
+    if (!shape_hit_distance_kind(s, light_shape_kind<TRAITS>(s), r, r.tmax, &t))
         return 0.f;
-    HitGeom g = shape_hit_geom(s, r, t);
+    HitGeom g = shape_hit_geom_kind(s, light_shape_kind<TRAITS>(s), r, t);
     float pdf = distance_sq(p, g.position) / (abs_dot(g.normal, neg(wi)) * s.area);
     if (isinf(pdf))
         pdf = 0.f;
@@ -828,6 +835,7 @@ struct LightSample { float3 position, wi; float pdf; float3 Li; };
 KYD_DEV bool light_is_delta(int kind) { return kind == KYD_LIGHT_POINT || kind == KYD_LIGHT_DIRECTION; }
 KYD_DEV float spherical_theta(float3 v) { return cr_acos(clamp_std(v.z, -1.f, 1.f)); } // ky.cpp:410
 
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV LightSample light_sample_Li(int light_index, const HitGeom& g, float2 u)
 {
     const DevLight& l = c_scene.lights[light_index];
@@ -836,24 +844,24 @@ KYD_DEV LightSample light_sample_Li(int light_index, const HitGeom& g, float2 u)
     s.wi = V3(0, 0, 0);
     s.pdf = 0;
     s.Li = KYD_BLACK;
-    if (KYD_LIGHT_KIND(l) == KYD_LIGHT_POINT) // ky.cpp:2825-2853
+    if (light_kind<TRAITS>(l) == KYD_LIGHT_POINT) // ky.cpp:2825-2853
     {
         s.position = l.position;
         s.wi = normalize(sub(l.position, g.position));
         s.pdf = 1.f;
         s.Li = cdiv(l.color, distance_sq(l.position, g.position));
     }
-    else if (KYD_LIGHT_KIND(l) == KYD_LIGHT_DIRECTION) // ky.cpp:2891-2901
+    else if (light_kind<TRAITS>(l) == KYD_LIGHT_DIRECTION) // ky.cpp:2891-2901
     {
         s.wi = neg(l.direction);
         s.position = add(g.position, mul(mul(s.wi, 2.f), l.world_radius));
         s.pdf = 1;
         s.Li = l.color;
     }
-    else if (KYD_LIGHT_KIND(l) == KYD_LIGHT_AREA) // ky.cpp:2964-2981
+    else if (light_kind<TRAITS>(l) == KYD_LIGHT_AREA) // ky.cpp:2964-2981
     {
         float3 lp, ln;
-        shape_sample_direction(c_scene.light_shape[light_index], g.position, g.normal, u, &lp, &ln, &s.pdf);
+        shape_sample_direction<TRAITS>(c_scene.light_shape[light_index], g.position, g.normal, u, &lp, &ln, &s.pdf);
         s.position = lp;
         if (!(s.pdf == 0 || msq(sub(lp, g.position)) == 0))
         {
@@ -874,12 +882,13 @@ KYD_DEV LightSample light_sample_Li(int light_index, const HitGeom& g, float2 u)
     return s;
 }
 
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV float light_pdf_Li(int light_index, const HitGeom& g, float3 wi)
 {
     const DevLight& l = c_scene.lights[light_index];
-    if (KYD_LIGHT_KIND(l) == KYD_LIGHT_AREA) // ky.cpp:2984-2988
-        return shape_pdf_direction(c_scene.light_shape[light_index], g.position, g.normal, wi);
-    if (KYD_LIGHT_KIND(l) == KYD_LIGHT_ENVIRONMENT) // ky.cpp:3043-3053
+    if (light_kind<TRAITS>(l) == KYD_LIGHT_AREA) // ky.cpp:2984-2988
+        return shape_pdf_direction<TRAITS>(c_scene.light_shape[light_index], g.position, g.normal, wi);
+    if (light_kind<TRAITS>(l) == KYD_LIGHT_ENVIRONMENT) // ky.cpp:3043-3053
     {
         float sin_theta = cr_sin(spherical_theta(wi));
         if (sin_theta == 0)
@@ -906,6 +915,7 @@ struct NeeRay
 
 // BSDF-sampled half: estimate_direct_lighting_by_bsdf (ky.cpp:3889-3930) when mis == false,
 // estimate_direct_lighting_by_bsdf_mis (ky.cpp:3968-4033) when mis == true
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, float2 random_bsdf, bool mis)
 {
     NeeRay q;
@@ -914,7 +924,7 @@ KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, 
     q.light = light_index;
     q.value = KYD_BLACK;
     const DevLight& l = c_scene.lights[light_index];
-    if (bsdf_is_delta(b.lobe) || light_is_delta(KYD_LIGHT_KIND(l)))
+    if (bsdf_is_delta(b.lobe) || light_is_delta(light_kind<TRAITS>(l)))
         return q;
     BsdfSample bs = bsdf_sample(b, g.wo, random_bsdf);
     float3 f_cos = mul(bs.f, abs_dot(bs.wi, g.normal));
@@ -930,7 +940,7 @@ KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, 
         q.value = cdiv(cmulc(f_cos, Li), bs.pdf);
     else
     {
-        float light_pdf = light_pdf_Li(light_index, g, bs.wi);
+        float light_pdf = light_pdf_Li<TRAITS>(light_index, g, bs.wi);
         if (!(light_pdf > 0))
             return q;
         q.value = cdiv(mul(cmulc(f_cos, Li), 2.f), bs.pdf + light_pdf);
@@ -956,6 +966,7 @@ KYD_DEV float3 nee_bsdf_resolve(const NeeRay& q, int hit_surface, float hit_t)
 
 // light-sampled half: estimate_direct_lighting_by_emitter (ky.cpp:3933-3962) when mis == false,
 // estimate_direct_lighting_by_emitter_mis (ky.cpp:4035-4074) when mis == true
+template <int TRAITS = TRAITS_ANY>
 KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index, float2 random_light, bool mis)
 {
     NeeRay q;
@@ -966,7 +977,7 @@ KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index,
     const DevLight& l = c_scene.lights[light_index];
     if (bsdf_is_delta(b.lobe))
         return q;
-    LightSample ls = light_sample_Li(light_index, g, random_light);
+    LightSample ls = light_sample_Li<TRAITS>(light_index, g, random_light);
     if (is_black(ls.Li) || (mis ? (ls.pdf <= 0) : (ls.pdf == 0)))
         return q;
     q.ref_query = true;
@@ -974,7 +985,7 @@ KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index,
     float3 wo_l = to_local(b.f, g.wo), wi_l = to_local(b.f, ls.wi);
     float3 f_eval;
     float bsdf_pdf_v;
-    const bool need_pdf = mis && !light_is_delta(KYD_LIGHT_KIND(l));
+    const bool need_pdf = mis && !light_is_delta(light_kind<TRAITS>(l));
     if (need_pdf)
         bsdf_eval_pdf_local(b, wo_l, wi_l, &f_eval, &bsdf_pdf_v);
     else

@@ -536,6 +536,23 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
     return cudaSuccess;
 }
 
+template <int TRAITS, bool HOT>
+static void launch_shade_lobes(int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
+{
+    k_shade<LOBE_LAMBERT, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_PHONG, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_MIRROR, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_FRESNEL, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+}
+
+static void launch_shade(int traits, bool hot, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
+{
+    if (!hot) launch_shade_lobes<TRAITS_ANY, false>(grid, stream, wp, w, counters, bounce);
+    else if (traits == TRAITS_AREA_RECTANGLE) launch_shade_lobes<TRAITS_AREA_RECTANGLE, true>(grid, stream, wp, w, counters, bounce);
+    else if (traits == TRAITS_AREA_SPHERE) launch_shade_lobes<TRAITS_AREA_SPHERE, true>(grid, stream, wp, w, counters, bounce);
+    else launch_shade_lobes<TRAITS_ANY, true>(grid, stream, wp, w, counters, bounce);
+}
+
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
                              cudaStream_t stream, int sm_count, uint64_t* launches, StageTimer* timer)
 {
@@ -545,6 +562,21 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
     const bool nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0;
     const int last_bounce = direct_only ? 0 : rp.max_depth;
+
+    // scene traits and the compiled-out headline configuration select the shade instantiation (kyd_wavefront.cuh)
+    int traits = TRAITS_ANY;
+    {
+        bool all_rect = scene.n_lights > 0, all_sphere = scene.n_lights > 0;
+        for (int l = 0; l < scene.n_lights; ++l)
+        {
+            const bool area = scene.lights[l].kind == KYD_LIGHT_AREA;
+            all_rect = all_rect && area && scene.light_shape[l].kind == KYD_SHAPE_RECTANGLE;
+            all_sphere = all_sphere && area && scene.light_shape[l].kind == KYD_SHAPE_SPHERE;
+        }
+        traits = all_rect ? TRAITS_AREA_RECTANGLE : all_sphere ? TRAITS_AREA_SPHERE : TRAITS_ANY;
+    }
+    const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler == KYD_SAMPLER_LCG48 &&
+                     !(rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE);
 
     // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
     const int grid256 = sm_count * 16, grid128 = sm_count * 24;
@@ -589,10 +621,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                     k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
                 T(-1);
                 T(StageTimer::SHADE);
-                k_shade<LOBE_LAMBERT><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
-                k_shade<LOBE_PHONG><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
-                k_shade<LOBE_MIRROR><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
-                k_shade<LOBE_FRESNEL><<<grid128, 128, 0, stream>>>(wp, w, counters, bounce);
+                launch_shade(traits, hot, grid128, stream, wp, w, counters, bounce);
                 T(-1);
                 *launches += 5;
                 if (nee)

@@ -326,9 +326,9 @@ KYD_DEV int light_draw_offset(int l, int direct_sample)
 
 // NEE + MIS set-up of one (vertex, light): the two draws and the first halves of the estimators
 // (ky.cpp:3864-3869, 3889-4074)
-KYD_DEV void light_sample_pair(const WaveParams& wp, const HitGeom& g, const Bsdf& b, int l, Sampler smp, NeeRay* qb, NeeRay* ql)
+template <int TRAITS>
+KYD_DEV void light_sample_pair(int ds, const HitGeom& g, const Bsdf& b, int l, Sampler smp, NeeRay* qb, NeeRay* ql)
 {
-    const int ds = wp.rp.direct_sample;
     float2 random_bsdf = smp.get_float2();
     float2 random_light = smp.get_float2();
 
@@ -340,15 +340,15 @@ KYD_DEV void light_sample_pair(const WaveParams& wp, const HitGeom& g, const Bsd
     qb->light = ql->light = l;
     if (ds == KYD_DS_BSDF)
     {
-        if (!light_is_delta(c_scene.lights[l].kind))
-            *qb = nee_bsdf_setup(g, b, l, smp.get_float2(), false);
+        if (!light_is_delta(light_kind<TRAITS>(c_scene.lights[l])))
+            *qb = nee_bsdf_setup<TRAITS>(g, b, l, smp.get_float2(), false);
     }
     else if (ds == KYD_DS_BSDF_MIS || ds == KYD_DS_BOTH_MIS)
-        *qb = nee_bsdf_setup(g, b, l, random_bsdf, true);
+        *qb = nee_bsdf_setup<TRAITS>(g, b, l, random_bsdf, true);
     if (ds == KYD_DS_LIGHT)
-        *ql = nee_light_setup(g, b, l, random_light, false);
+        *ql = nee_light_setup<TRAITS>(g, b, l, random_light, false);
     else if (ds == KYD_DS_LIGHT_MIS || ds == KYD_DS_BOTH_MIS)
-        *ql = nee_light_setup(g, b, l, random_light, true);
+        *ql = nee_light_setup<TRAITS>(g, b, l, random_light, true);
 }
 
 // writes the light-sampling line of (light, path): sectors 0-1 always, sector 2 only for a live BSDF-sampled query
@@ -370,10 +370,16 @@ KYD_DEV void store_nee_line(float4* line, const NeeRay& qb, const NeeRay& ql, fl
 struct ShadeCounts { unsigned ref_rays; };
 
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
-template <int LOBE>
+// HOT: the headline configuration (path_tracing_iteration_t, both_mis, LCG48 sampler, light-sample inside shade)
+// with those run-time switches compiled out; !HOT reads them from the parameters
+template <int LOBE, int TRAITS, bool HOT>
 KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee,
                           ShadeCounts* counts)
 {
+    const int ds = HOT ? (int)KYD_DS_BOTH_MIS : wp.rp.direct_sample;
+    const bool direct_only = HOT ? false : wp.direct_only != 0;
+    const bool split_light_sample = HOT ? false : wp.split_light_sample != 0;
+    const bool debug_sampler = HOT ? false : wp.rp.sampler == KYD_SAMPLER_DEBUG;
     float4* p = path_line(w, slot);
     PathState st;
     unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
@@ -396,7 +402,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     float3 next_o = st.o, next_d = st.d, next_beta = beta;
     int next_flags = 0;
     unsigned long long rng_state = st.rng;
-    if (bounce < wp.rp.max_depth + wp.direct_only)
+    if (bounce < wp.rp.max_depth + (direct_only ? 1 : 0))
     {
         const DevMaterial& m = c_scene.materials[c_scene.surf_material[surface]];
         Bsdf b;
@@ -411,14 +417,14 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
         else { b.a = m.specular; b.t = m.transmission; b.eta_t = m.eta; }
 
         Sampler smp;
-        smp.debug = (wp.rp.sampler == KYD_SAMPLER_DEBUG);
+        smp.debug = debug_sampler;
         smp.state = rng_state;
 
         if (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG)
         {
-            if (wp.rp.direct_sample != KYD_DS_IDLE && n_lights > 0)
+            if (ds != KYD_DS_IDLE && n_lights > 0)
             {
-                if (wp.split_light_sample)
+                if (split_light_sample)
                 {
                     // vertex record for the light-sample stage
                     float4* v = vertex_line(w, slot);
@@ -434,7 +440,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                 {
                     // the common case keeps both queries in registers and writes nothing when neither can contribute
                     NeeRay qb, ql;
-                    light_sample_pair(wp, g, b, 0, smp, &qb, &ql);
+                    light_sample_pair<TRAITS>(ds, g, b, 0, smp, &qb, &ql);
                     counts->ref_rays += (qb.ref_query ? 1u : 0u) + (ql.ref_query ? 1u : 0u);
                     // (beta * 0 is 0 only for finite beta: a non-finite throughput keeps the reference's NaN)
                     const bool finite_beta = isfinite(beta.x) && isfinite(beta.y) && isfinite(beta.z);
@@ -451,19 +457,19 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                     for (int l = 0; l < n_lights; ++l)
                     {
                         NeeRay qb, ql;
-                        light_sample_pair(wp, g, b, l, ls, &qb, &ql);
+                        light_sample_pair<TRAITS>(ds, g, b, l, ls, &qb, &ql);
                         store_nee_line(nee_line(w, wp.plane, l, slot), qb, ql, beta);
-                        ls.skip(4 + ((wp.rp.direct_sample == KYD_DS_BSDF && !light_is_delta(c_scene.lights[l].kind)) ? 2 : 0));
+                        ls.skip(4 + ((ds == KYD_DS_BSDF && !light_is_delta(c_scene.lights[l].kind)) ? 2 : 0));
                     }
                     new_pending = n_lights;
                 }
                 *out_nee = new_pending > 0;
             }
             // sample_all_light draws 4 floats per light, plus 2 per non-delta light in `bsdf` mode
-            smp.skip(4 * n_lights + (wp.rp.direct_sample == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
+            smp.skip(4 * n_lights + (ds == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
         }
 
-        if (!wp.direct_only)
+        if (!direct_only)
         {
             BsdfSample bs = bsdf_sample(b, g.wo, smp.get_float2());
             if (!(is_black(bs.f) || bs.pdf == 0.f))
@@ -496,7 +502,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     store_path_tail(p, next_beta, Lo, rng_state);
 }
 
-template <int LOBE>
+template <int LOBE, int TRAITS, bool HOT>
 KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
 {
     const int parity = bounce & 1;
@@ -525,7 +531,7 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
         bool alive = false, wants_nee = false;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         if (slot_cur >= 0)
-            shade_vertex<LOBE>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &counts);
+            shade_vertex<LOBE, TRAITS, HOT>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &counts);
         push.commit(out_queues);
         push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
         slot_cur = slot_next;
@@ -536,10 +542,10 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
 // shades most vertices, does not pay for Phong's pow() or the dielectric's Fresnel terms)
-template <int LOBE>
+template <int LOBE, int TRAITS, bool HOT>
 __global__ void __launch_bounds__(SHADE_THREADS, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
-    shade_queue<LOBE>(wp, w, counters, bounce);
+    shade_queue<LOBE, TRAITS, HOT>(wp, w, counters, bounce);
 }
 
 // ---- light-sample as its own stage (KYD_FLAG_SPLIT_LIGHT_SAMPLE): one thread per (vertex, light) -------------
@@ -574,7 +580,7 @@ KYD_DEV void light_sample_queue(const WaveParams& wp, const WaveBuffers& w, DevC
         smp.state = (unsigned long long)__float_as_uint(rng4.x) | ((unsigned long long)__float_as_uint(rng4.y) << 32);
         smp.skip(light_draw_offset(l, wp.rp.direct_sample));
         NeeRay qb, ql;
-        light_sample_pair(wp, g, b, l, smp, &qb, &ql);
+        light_sample_pair<TRAITS_ANY>(wp.rp.direct_sample, g, b, l, smp, &qb, &ql);
         store_nee_line(nee_line(w, wp.plane, l, slot), qb, ql, V3(vb.x, vb.y, vb.z));
     }
 }
