@@ -284,7 +284,7 @@ KYD_DEV float plastic_random(float3 p, float3 wo)
 // Scene traits: which light kinds / light shapes can occur, known when the scene is uploaded.  Kernels instantiated
 // for a restricted scene drop the code of the other kinds (the shade kernels are instruction-fetch sensitive:
 // profiles/r01_ab_variants.txt).  0 = anything; 1 = area lights on rectangles only (Cornell); 2 = area lights on
-// spheres only (Veach).
+// spheres only (Veach).  TRAITS_AREA_RECTANGLE additionally means: exactly ONE light (no light loop).
 enum { TRAITS_ANY = 0, TRAITS_AREA_RECTANGLE = 1, TRAITS_AREA_SPHERE = 2 };
 template <int TRAITS> KYD_DEV int light_kind(const DevLight& l) { return TRAITS == TRAITS_ANY ? l.kind : KYD_LIGHT_AREA; }
 template <int TRAITS> KYD_DEV int light_shape_kind(const DevShape& s)

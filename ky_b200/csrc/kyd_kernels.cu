@@ -573,7 +573,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             all_rect = all_rect && area && scene.light_shape[l].kind == KYD_SHAPE_RECTANGLE;
             all_sphere = all_sphere && area && scene.light_shape[l].kind == KYD_SHAPE_SPHERE;
         }
-        traits = all_rect ? TRAITS_AREA_RECTANGLE : all_sphere ? TRAITS_AREA_SPHERE : TRAITS_ANY;
+        traits = (all_rect && scene.n_lights == 1) ? TRAITS_AREA_RECTANGLE : all_sphere ? TRAITS_AREA_SPHERE : TRAITS_ANY;
     }
     const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler == KYD_SAMPLER_LCG48 &&
                      !(rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE);

@@ -436,7 +436,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                     v[V_BETA] = make_float4(beta.x, beta.y, beta.z, 0.f);
                     new_pending = n_lights;
                 }
-                else if (n_lights == 1)
+                else if (TRAITS == TRAITS_AREA_RECTANGLE || n_lights == 1)
                 {
                     // the common case keeps both queries in registers and writes nothing when neither can contribute
                     NeeRay qb, ql;
@@ -451,7 +451,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                         new_pending = 1;
                     }
                 }
-                else
+                else if (TRAITS != TRAITS_AREA_RECTANGLE)
                 {
                     Sampler ls = smp;
                     for (int l = 0; l < n_lights; ++l)
