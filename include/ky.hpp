@@ -392,6 +392,37 @@ private:
 };
 
 // ---- film (ky.cpp:1545-1836) ---------------------------------------------------------------------
+// one device context per process and CUDA device, created on first use
+class device_t
+{
+public:
+    static device_t& instance(int cuda_device = -1)
+    {
+        static device_t dev(cuda_device < 0 ? env_device() : cuda_device);
+        return dev;
+    }
+    kyd_ctx* ctx() const { return ctx_; }
+    void check(int rc) const
+    {
+        if (rc != KYD_OK)
+            throw std::runtime_error(std::string("kyd: ") + kyd_last_error(ctx_));
+    }
+    ~device_t() { kyd_destroy(ctx_); }
+
+private:
+    explicit device_t(int cuda_device)
+    {
+        if (kyd_create(&ctx_, cuda_device) != KYD_OK)
+            throw std::runtime_error(std::string("kyd_create: ") + kyd_last_error(nullptr));
+    }
+    static int env_device()
+    {
+        const char* e = std::getenv("KY_CUDA_DEVICE");
+        return e ? std::atoi(e) : 0;
+    }
+    kyd_ctx* ctx_{};
+};
+
 constexpr float clamp01(float x) { return std::clamp(x, 0.f, 1.f); }
 inline color_t clamp01(color_t c) { return color_t(clamp01(c.r), clamp01(c.g), clamp01(c.b)); }
 inline uint8_t gamma_encoding(float x) { return (uint8_t)(std::pow((double)clamp01(x), 1 / 2.2) * 255 + .5); }
@@ -423,11 +454,43 @@ public:
 
     const float* data() const { return &pixels_[0].r; }
 
-    // writes <filename>.bmp (24-bit BGR, bottom-up, gamma 1/2.2 like ky.cpp:1661-1737); no viewer is launched
+    // writes <filename>.bmp (24-bit BGR, bottom-up, gamma 1/2.2), or <filename>.hdr with KY_OUTPUT_HDR, like
+    // ky.cpp:1623-1659; the per-pixel work runs on the device (film output stage); no viewer is launched
     virtual bool store_image(std::string filename) const
     {
-        return store_bmp(filename + ".bmp");
+#ifdef KY_OUTPUT_HDR
+        return store_device(filename + ".hdr", KYD_FILM_RGBE);
+#else
+        return store_device(filename + ".bmp", KYD_FILM_BMP24);
+#endif
     }
+
+    // header from kyd_film_header, body from the device (kyd_film_encode); KYD_FILM_GAMMA8 is printed as a P3 ppm
+    bool store_device(const std::string& path, int format) const
+    {
+        const int64_t bytes = kyd_film_body_bytes(format, width_, height_);
+        uint8_t header[128];
+        const int header_bytes = kyd_film_header(format, width_, height_, header, (int)sizeof(header));
+        if (bytes < 0 || header_bytes < 0) return false;
+        std::vector<uint8_t> body((size_t)bytes);
+        device_t& dev = device_t::instance();
+        dev.check(kyd_film_encode(dev.ctx(), data(), width_, height_, format, body.data()));
+        std::ofstream out(path, std::ios::binary);
+        if (!out) return false;
+        out.write((const char*)header, header_bytes);
+        if (format == KYD_FILM_GAMMA8)
+        {
+            std::string text;
+            text.reserve(body.size() * 4);
+            for (uint8_t v : body) { text += std::to_string((int)v); text += ' '; }
+            out.write(text.data(), (std::streamsize)text.size());
+        }
+        else
+            out.write((const char*)body.data(), (std::streamsize)body.size());
+        return (bool)out;
+    }
+
+    // host-side writers with the reference's arithmetic (store_bmp_impl / store_ppm_impl / store_hdr_impl)
 
     bool store_bmp(const std::string& path) const
     {
@@ -1145,37 +1208,6 @@ enum class integrator_enum_t
     stochastic_raytracing,
     simple_path_tracing_recursion,
     path_tracing_recursion, path_tracing_recursion_defered, path_tracing_iteration,
-};
-
-// one device context per process and CUDA device, created on first use
-class device_t
-{
-public:
-    static device_t& instance(int cuda_device = -1)
-    {
-        static device_t dev(cuda_device < 0 ? env_device() : cuda_device);
-        return dev;
-    }
-    kyd_ctx* ctx() const { return ctx_; }
-    void check(int rc) const
-    {
-        if (rc != KYD_OK)
-            throw std::runtime_error(std::string("kyd: ") + kyd_last_error(ctx_));
-    }
-    ~device_t() { kyd_destroy(ctx_); }
-
-private:
-    explicit device_t(int cuda_device)
-    {
-        if (kyd_create(&ctx_, cuda_device) != KYD_OK)
-            throw std::runtime_error(std::string("kyd_create: ") + kyd_last_error(nullptr));
-    }
-    static int env_device()
-    {
-        const char* e = std::getenv("KY_CUDA_DEVICE");
-        return e ? std::atoi(e) : 0;
-    }
-    kyd_ctx* ctx_{};
 };
 
 class integrator_t

@@ -223,6 +223,29 @@ int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64
 /* size in paths of one wavefront (0 = choose from the film size); tuning knob, results do not depend on it */
 int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths);
 
+/* ---- film output stage: the step right after the path (replaces the per-pixel loops of
+   film_t::store_ppm_impl / store_bmp_impl / store_hdr_impl, ky.cpp:1661-1782).  The device turns the float
+   film into the BODY bytes of the image file; kyd_film_header() gives the bytes the reference writes in front.
+     KYD_FILM_GAMMA8 : 3 bytes/pixel, R G B, rows top-down; byte = gamma_encoding(x) =
+                       (uint8_t)(pow((double)clamp01(x), 1/2.2) * 255 + .5)  (ky.cpp:1548).  The numbers the
+                       reference prints into a P3 ppm (ky.cpp:1669-1681); header = "P3\n<w> <h>\n255\n".
+     KYD_FILM_BMP24  : the same bytes as B G R, rows bottom-up, lines NOT padded to 4 bytes although the
+                       header's file size is computed from padded lines (ky.cpp:1719-1733, reference quirk kept).
+     KYD_FILM_RGBE   : 4 bytes/pixel Radiance RGBE, flat (no RLE), rows top-down (ky.cpp:1739-1782).
+   NaN / out-of-range float->uint8 conversions follow the reference binary on x86-64 (cvttss2si, low byte). */
+enum kyd_film_format { KYD_FILM_GAMMA8 = 0, KYD_FILM_BMP24 = 1, KYD_FILM_RGBE = 2 };
+
+/* body size in bytes (3*w*h or 4*w*h); -1 for an unknown format or non-positive size */
+int64_t kyd_film_body_bytes(int format, int width, int height);
+/* writes the file header into `out` (capacity `cap`), returns its length, or -1.  Pure host function. */
+int kyd_film_header(int format, int width, int height, uint8_t* out, int cap);
+/* host film (width*height*3 floats, row-major top-down) -> host body bytes; copies in, encodes on the device, copies out */
+int kyd_film_encode(kyd_ctx* ctx, const float* film_rgb, int width, int height, int format, uint8_t* out_body);
+/* same with DEVICE pointers on the context's device: a film left resident by kyd_render_device is encoded without
+   ever crossing PCIe as floats.  Stream semantics as kyd_render_device. */
+int kyd_film_encode_device(kyd_ctx* ctx, const float* film_rgb_device, int width, int height, int format,
+                           uint8_t* out_body_device, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,7 +92,11 @@ class EntryParams(C.Structure):
 
 
 KYD_SYMBOLS = ["kyd_create", "kyd_destroy", "kyd_last_error", "kyd_upload_scene", "kyd_render",
-               "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest"]
+               "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest",
+               "kyd_film_body_bytes", "kyd_film_header", "kyd_film_encode", "kyd_film_encode_device"]
+
+# kyd_film_format
+FILM_GAMMA8, FILM_BMP24, FILM_RGBE = 0, 1, 2
 
 _kyd = None
 _host = None
@@ -126,6 +130,11 @@ def kyd():
         l.kyd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         l.kyd_set_wave_paths.argtypes = [C.c_void_p, C.c_int64]
         l.kyd_selftest.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+        l.kyd_film_body_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        l.kyd_film_body_bytes.restype = C.c_int64
+        l.kyd_film_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        l.kyd_film_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        l.kyd_film_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _kyd = l
     return _kyd
 
@@ -259,6 +268,20 @@ class Device:
     def clamp_device(self, device_ptr, n, stream=None):
         self._check(kyd().kyd_clamp_device(self._ctx, C.c_void_p(device_ptr), n, C.c_void_p(stream or 0)))
 
+    def film_encode(self, film, fmt):
+        """Film output stage: host film[h, w, 3] float32 -> body bytes (uint8) of the reference's ppm / bmp / hdr file."""
+        film = np.ascontiguousarray(film, np.float32)
+        h, w = film.shape[:2]
+        n = kyd().kyd_film_body_bytes(fmt, w, h)
+        if n < 0:
+            raise ValueError("unknown film format or empty film")
+        out = np.empty(n, np.uint8)
+        self._check(kyd().kyd_film_encode(self._ctx, film.ctypes.data_as(C.c_void_p), w, h, fmt, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def film_encode_device(self, film_ptr, width, height, fmt, out_ptr, stream=None):
+        self._check(kyd().kyd_film_encode_device(self._ctx, C.c_void_p(film_ptr), width, height, fmt, C.c_void_p(out_ptr), C.c_void_p(stream or 0)))
+
     def set_wave_paths(self, paths):
         self._check(kyd().kyd_set_wave_paths(self._ctx, paths))
 
@@ -271,6 +294,15 @@ class Device:
         s = Stats()
         self._check(kyd().kyd_get_stats(self._ctx, C.byref(s)))
         return s
+
+
+def film_header(fmt, width, height):
+    """The bytes the reference writes in front of the body (pure host function of libkyd)."""
+    buf = (C.c_uint8 * 128)()
+    n = kyd().kyd_film_header(fmt, width, height, buf, 128)
+    if n < 0:
+        raise ValueError("unknown film format or empty film")
+    return bytes(buf[:n])
 
 
 def render_entry(name, sub_width=0, sub_height=0, spp=0, depth=0, render=True):

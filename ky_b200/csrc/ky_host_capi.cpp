@@ -126,4 +126,40 @@ int ky_host_render_entry(const char* name, const ky_entry_params* params, float*
     }
 }
 
+// film_t writers on caller-provided pixels: kind 0 = store_image (device film stage: <path>.bmp, or .hdr when the
+// library is built with KY_OUTPUT_HDR), 1/2/3 = device-encoded ppm / bmp / hdr written to `path` as given,
+// 11/12/13 = the host-side writers (reference arithmetic on the CPU) for ppm / bmp / hdr.
+int ky_host_film_store(int kind, const char* path, int width, int height, const float* rgb)
+{
+    try
+    {
+        film_t film(width, height);
+        for (int y = 0; y < height; ++y)
+            for (int x = 0; x < width; ++x)
+            {
+                const float* p = rgb + 3 * ((size_t)y * width + x);
+                film.set_color(x, y, color_t(p[0], p[1], p[2]));
+            }
+        bool ok = false;
+        switch (kind)
+        {
+        case 0: ok = film.store_image(path); break;
+        case 1: ok = film.store_device(path, KYD_FILM_GAMMA8); break;
+        case 2: ok = film.store_device(path, KYD_FILM_BMP24); break;
+        case 3: ok = film.store_device(path, KYD_FILM_RGBE); break;
+        case 11: ok = film.store_ppm(path); break;
+        case 12: ok = film.store_bmp(path); break;
+        case 13: ok = film.store_hdr(path); break;
+        default: g_error = "unknown film writer"; return 2;
+        }
+        if (!ok) { g_error = std::string("cannot write ") + path; return 1; }
+        return 0;
+    }
+    catch (const std::exception& e)
+    {
+        g_error = e.what();
+        return 1;
+    }
+}
+
 } // extern "C"

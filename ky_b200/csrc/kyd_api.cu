@@ -26,6 +26,8 @@ struct kyd_ctx
     size_t film_capacity = 0;       // floats
     float* film_pinned = nullptr;   // pinned bounce buffer for the device->host copy
     size_t pinned_capacity = 0;
+    uint8_t* body_dev = nullptr;    // encoded image body for kyd_film_encode (host destination)
+    size_t body_capacity = 0;
 
     DevCounters* counters_dev = nullptr;
     DevCounters* counters_pinned = nullptr;
@@ -88,6 +90,7 @@ int ensure_pinned(kyd_ctx* ctx, size_t floats)
     if (floats <= ctx->pinned_capacity)
         return KYD_OK;
     if (ctx->film_pinned) cudaFreeHost(ctx->film_pinned);
+    if (ctx->body_dev) cudaFree(ctx->body_dev);
     ctx->film_pinned = nullptr;
     ctx->pinned_capacity = 0;
     KYD_CUDA(ctx, cudaMallocHost(&ctx->film_pinned, floats * sizeof(float)));
@@ -250,6 +253,7 @@ void kyd_destroy(kyd_ctx* ctx)
     free_wave_buffers(ctx->wave);
     if (ctx->film_dev) cudaFree(ctx->film_dev);
     if (ctx->film_pinned) cudaFreeHost(ctx->film_pinned);
+    if (ctx->body_dev) cudaFree(ctx->body_dev);
     if (ctx->counters_dev) cudaFree(ctx->counters_dev);
     if (ctx->counters_pinned) cudaFreeHost(ctx->counters_pinned);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -381,6 +385,81 @@ int kyd_clamp_device(kyd_ctx* ctx, float* film_rgb_device, int64_t n, void* cuda
     if (n > 0) launch_clamp(film_rgb_device, n, stream);
     KYD_CUDA(ctx, cudaGetLastError());
     if (!cuda_stream) KYD_CUDA(ctx, cudaStreamSynchronize(stream));
+    return KYD_OK;
+}
+
+int64_t kyd_film_body_bytes(int format, int width, int height)
+{
+    if (width <= 0 || height <= 0) return -1;
+    if (format == KYD_FILM_GAMMA8 || format == KYD_FILM_BMP24) return (int64_t)width * height * 3;
+    if (format == KYD_FILM_RGBE) return (int64_t)width * height * 4;
+    return -1;
+}
+
+int kyd_film_header(int format, int width, int height, uint8_t* out, int cap)
+{
+    if (!out || kyd_film_body_bytes(format, width, height) < 0) return -1;
+    char text[96];
+    int n = 0;
+    if (format == KYD_FILM_GAMMA8)
+        n = snprintf(text, sizeof(text), "P3\n%d %d\n%d\n", width, height, 255);                       // ky.cpp:1673
+    else if (format == KYD_FILM_RGBE)
+        n = snprintf(text, sizeof(text), "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", height, width); // ky.cpp:1745-1748
+    else
+    {
+        // ky.cpp:1692-1733: "BM" + 13 little-endian words; the file size counts padded lines although the body is unpadded
+        const uint32_t padded = ((uint32_t)width * 3u + 3u) & ~3u;
+        const uint32_t words[13] = { 14u + 40u + padded * (uint32_t)height, 0u, 54u, 40u, (uint32_t)width, (uint32_t)height,
+                                     1u | (24u << 16), 0u, 0u, 0u, 0u, 0u, 0u };
+        if (cap < 54) return -1;
+        out[0] = 'B'; out[1] = 'M';
+        memcpy(out + 2, words, sizeof(words));
+        return 54;
+    }
+    if (n <= 0 || n > cap) return -1;
+    memcpy(out, text, (size_t)n);
+    return n;
+}
+
+int kyd_film_encode_device(kyd_ctx* ctx, const float* film_rgb_device, int width, int height, int format, uint8_t* out_body_device, void* cuda_stream)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (kyd_film_body_bytes(format, width, height) < 0) return fail(ctx, KYD_ERR_INVALID, "unknown film format or non-positive film size");
+    if (!film_rgb_device || !out_body_device) return fail(ctx, KYD_ERR_INVALID, "film / body pointer is null");
+    if (((uintptr_t)film_rgb_device & 15u) || ((uintptr_t)out_body_device & 3u))
+        return fail(ctx, KYD_ERR_INVALID, "film must be 16-byte aligned and the body 4-byte aligned");
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
+    KYD_CUDA(ctx, launch_film_encode(ctx->device, ctx->sm_count, film_rgb_device, width, height, format, out_body_device, stream));
+    if (!cuda_stream) KYD_CUDA(ctx, cudaStreamSynchronize(stream));
+    return KYD_OK;
+}
+
+int kyd_film_encode(kyd_ctx* ctx, const float* film_rgb, int width, int height, int format, uint8_t* out_body)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    const int64_t bytes = kyd_film_body_bytes(format, width, height);
+    if (bytes < 0) return fail(ctx, KYD_ERR_INVALID, "unknown film format or non-positive film size");
+    if (!film_rgb || !out_body) return fail(ctx, KYD_ERR_INVALID, "film / body pointer is null");
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t floats = (size_t)width * height * 3;
+    int rc;
+    if ((rc = ensure_film(ctx, floats)) != KYD_OK) return rc;
+    if ((rc = ensure_pinned(ctx, floats)) != KYD_OK) return rc;   // floats * 4 >= bytes: one bounce buffer serves both ways
+    if ((size_t)bytes > ctx->body_capacity)
+    {
+        if (ctx->body_dev) cudaFree(ctx->body_dev);
+        ctx->body_dev = nullptr;
+        ctx->body_capacity = 0;
+        KYD_CUDA(ctx, cudaMalloc(&ctx->body_dev, (size_t)bytes));
+        ctx->body_capacity = (size_t)bytes;
+    }
+    memcpy(ctx->film_pinned, film_rgb, floats * sizeof(float));
+    KYD_CUDA(ctx, cudaMemcpyAsync(ctx->film_dev, ctx->film_pinned, floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    KYD_CUDA(ctx, launch_film_encode(ctx->device, ctx->sm_count, ctx->film_dev, width, height, format, ctx->body_dev, ctx->stream));
+    KYD_CUDA(ctx, cudaMemcpyAsync(ctx->film_pinned, ctx->body_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    KYD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out_body, ctx->film_pinned, (size_t)bytes);
     return KYD_OK;
 }
 

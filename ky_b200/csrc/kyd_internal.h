@@ -60,6 +60,10 @@ void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 
+// film output stage (kyd_film.cu): float film -> body bytes of `format` (kyd_film_format); film_dev 16-byte and
+// out_dev 4-byte aligned
+cudaError_t launch_film_encode(int device, int sm_count, const float* film_dev, int width, int height, int format, uint8_t* out_dev, cudaStream_t stream);
+
 void free_wave_buffers(WaveBuffers& w);
 // (re)allocates the wavefront buffers for `capacity` path slots and `lights` lights; returns a cudaError_t
 int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights);

@@ -459,4 +459,23 @@ int kyref_light_sample(int scene, int scene_flags, int light_index, int n, const
     return 0;
 }
 
+// film output stage (ky.cpp:1548, 1661-1782): the reference's own static writers on caller-provided floats;
+// format 0 = ppm (text), 1 = bmp, 2 = hdr.  gamma: n floats -> n bytes through gamma_encoding().
+int kyref_store_film(int format, const char* path, int width, int height, const float* floats)
+{
+    switch (format)
+    {
+    case 0: return film_t::store_ppm_impl(path, width, height, 3, floats) ? 0 : 1;
+    case 1: return film_t::store_bmp_impl(path, width, height, 3, floats) ? 0 : 1;
+    case 2: return film_t::store_hdr_impl(path, width, height, 3, floats) ? 0 : 1;
+    }
+    return 2;
+}
+
+void kyref_gamma_encoding(long long n, const float* in, unsigned char* out)
+{
+    for (long long i = 0; i < n; ++i)
+        out[i] = gamma_encoding(in[i]);
+}
+
 } // extern "C"

@@ -23,7 +23,10 @@ CONFIGS = [
     ("-- pixel kernel: veach 1280x720 PT d5 both_mis", ky.SCENE_VEACH, 0, 1280, 720, ky.INT_PT_ITERATION, 5, ky.DS_BOTH_MIS, -1024),
     ("-- pixel kernel: cornell 1024x768 pt_recursion d5", ky.SCENE_CORNELL, ky.CB_DEFAULT, 1024, 768, ky.INT_PT_RECURSION, 5, ky.DS_BOTH_MIS, -64),
 ]
+ONLY = os.environ.get("KYD_BENCH_ONLY")
 for name, sid, flags, w, h, integ, depth, ds, spp in CONFIGS:
+    if ONLY and ONLY not in name:
+        continue
     fl = ky.FLAG_FUSED if spp < 0 else int(os.environ.get("KYD_BENCH_FLAGS", "0"))
     spp = abs(spp)
     scene = ky.Scene(sid, w, h, flags)

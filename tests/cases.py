@@ -45,3 +45,27 @@ def film_cases():
 def make_scene(scene_key, w=W, h=H):
     sid, flags = SCENES[scene_key]
     return ky.Scene(sid, w, h, flags)
+
+
+# ---- film output stage -------------------------------------------------------------------------------------------
+FILM_EDGE_VALUES = [0.0, -0.0, 1.0, 1.5, -3.7, float("nan"), float("inf"), float("-inf"), 1e-33, 1e-32, 9.9e-33, 1e-20,
+                    300.0, 1e30, -1e30, 3e9, -3e9, 0.5, 2.0 ** -126, 1e-45, 0.0031308, 0.999999, 1.0000001, 255.0, 256.0]
+
+
+def stage_film(width, height, seed, scale=False):
+    """A film for the output stage: uniform values, the edge values above sprinkled in, optionally wild magnitudes."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    f = rng.random((height, width, 3)).astype(np.float32)
+    if scale:
+        f *= rng.choice(np.array([1, 10, 1e-3, 1e5, -1, 1e-30, 1e25], np.float32), size=f.shape)
+    flat = f.reshape(-1)
+    edge = np.array(FILM_EDGE_VALUES, np.float32)
+    for k in range(0, flat.size - edge.size, max(edge.size + 7, flat.size // 5)):
+        flat[k:k + edge.size] = edge if (k // 7) % 2 == 0 else edge[::-1]
+    return f
+
+
+# (name, width, height, seed, scale): odd sizes so that 3*w is not a multiple of 4 and words straddle bmp lines
+STAGE_FILMS = [("37x21", 37, 21, 1, False), ("37x21s", 37, 21, 2, True), ("1x1", 1, 1, 3, False), ("5x3", 5, 3, 4, True),
+               ("64x48", 64, 48, 5, False), ("3x7", 3, 7, 6, True)]

@@ -33,6 +33,16 @@ def films():
     return out
 
 
+def film_stage():
+    """Files written by the reference's own store_ppm_impl / store_bmp_impl / store_hdr_impl for cases.STAGE_FILMS."""
+    out = {}
+    for name, w, h, seed, scale in cases.STAGE_FILMS:
+        f = cases.stage_film(w, h, seed, scale)
+        for fmt, ext in ((0, "ppm"), (1, "bmp"), (2, "hdr")):
+            out[f"{name}.{ext}"] = np.frombuffer(kyref.store_film(fmt, w, h, f), np.uint8)
+    return out
+
+
 def rng(seed):
     return np.random.default_rng(seed)
 
@@ -124,6 +134,8 @@ def kats():
 
 if __name__ == "__main__":
     assert kyref.available("det") and kyref.available("verbatim"), "build oracle/_ref first (oracle/ref/build_ref.sh)"
-    np.savez_compressed(os.path.join(HERE, "golden_films.npz"), **films())
-    np.savez_compressed(os.path.join(HERE, "golden_kat.npz"), **kats())
+    if "--film-stage-only" not in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "golden_films.npz"), **films())
+        np.savez_compressed(os.path.join(HERE, "golden_kat.npz"), **kats())
+    np.savez_compressed(os.path.join(HERE, "golden_film_stage.npz"), **film_stage())
     print("wrote", os.listdir(HERE))

@@ -86,3 +86,23 @@ def light_sample(scene, light_index, inp):
     out = np.zeros((inp.shape[0], 11), np.float32)
     lib().kyo_light_sample(scene.desc_ptr, C.c_int(light_index), C.c_int(inp.shape[0]), _fp(inp), _fp(out))
     return out
+
+
+def film_encode(fmt, film):
+    """Body bytes of the reference's ppm (values) / bmp / hdr file for film[h, w, 3]."""
+    film = np.ascontiguousarray(film, np.float32)
+    h, w = film.shape[:2]
+    lib().kyo_film_body_bytes.restype = C.c_int64
+    n = lib().kyo_film_body_bytes(C.c_int(fmt), C.c_int(w), C.c_int(h))
+    assert n >= 0
+    out = np.zeros(n, np.uint8)
+    rc = lib().kyo_film_encode(C.c_int(fmt), C.c_int(w), C.c_int(h), film.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def gamma_encoding(x):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.size, np.uint8)
+    lib().kyo_gamma_encoding(C.c_int64(x.size), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.reshape(x.shape)

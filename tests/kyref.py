@@ -137,3 +137,23 @@ def light_sample(scene, scene_flags, light_index, inp, kind="det"):
     if rc != 0:
         raise IndexError("light index")
     return out
+
+
+def store_film(fmt, width, height, floats, kind="verbatim"):
+    """The reference's own store_ppm_impl (0) / store_bmp_impl (1) / store_hdr_impl (2): returns the file's bytes."""
+    import tempfile
+    floats = np.ascontiguousarray(floats, np.float32)
+    assert floats.size == width * height * 3
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "film.out")
+        rc = lib(kind).kyref_store_film(C.c_int(fmt), path.encode(), C.c_int(width), C.c_int(height), floats.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        with open(path, "rb") as f:
+            return f.read()
+
+
+def gamma_encoding(x, kind="verbatim"):
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.size, np.uint8)
+    lib(kind).kyref_gamma_encoding(C.c_longlong(x.size), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out.reshape(x.shape)
