@@ -90,7 +90,6 @@ int ensure_pinned(kyd_ctx* ctx, size_t floats)
     if (floats <= ctx->pinned_capacity)
         return KYD_OK;
     if (ctx->film_pinned) cudaFreeHost(ctx->film_pinned);
-    if (ctx->body_dev) cudaFree(ctx->body_dev);
     ctx->film_pinned = nullptr;
     ctx->pinned_capacity = 0;
     KYD_CUDA(ctx, cudaMallocHost(&ctx->film_pinned, floats * sizeof(float)));

@@ -64,6 +64,7 @@ def test_gamma_encoding_every_float_of_unit_interval(dev):
         n3 = (n + 2) // 3 * 3
         x = torch.arange(first, first + n3, dtype=torch.int64, device="cuda").clamp_(max=0x3F800000)
         film = x.to(torch.int32).view(torch.float32).contiguous()
+        torch.cuda.synchronize()  # the context's own stream does not wait for torch's
         dev.film_encode_device(film.data_ptr(), n3 // 3, 1, ky.FILM_GAMMA8, body.data_ptr())
         torch.cuda.synchronize()
         want = torch.searchsorted(bits, x, right=True) - 1
