@@ -560,7 +560,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     const long long npix_total = (long long)rp.width * rp.height;
     const int nsamples = rp.sample_end - rp.sample_begin;
     const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
-    const bool nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0;
+    bool nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0;
     const int last_bounce = direct_only ? 0 : rp.max_depth;
 
     // scene traits and the compiled-out headline configuration select the shade instantiation (kyd_wavefront.cuh)
@@ -577,6 +577,9 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     }
     const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler == KYD_SAMPLER_LCG48 &&
                      !(rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE);
+    // the headline kernels trace a single light's queries inside shade: no light-sampling lines, no shadow stage
+    if (hot && scene.n_lights == 1)
+        nee = false;
 
     // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
     const int grid256 = sm_count * 16, grid128 = sm_count * 24;

@@ -367,14 +367,37 @@ KYD_DEV void store_nee_line(float4* line, const NeeRay& qb, const NeeRay& ql, fl
 }
 
 // what shade did, for the statistics: reference-equivalent scene queries it accounted for
-struct ShadeCounts { unsigned ref_rays; };
+struct ShadeCounts { unsigned ref_rays, traced; };
+
+
+// the scene queries of one (vertex, light) and the estimator's second half, inside shade: closest-hit query for the
+// BSDF-sampled direction, occlusion query for the light-sampled point; Lb, Ll or 0.5 Lb + 0.5 Ll (ky.cpp:4083)
+KYD_DEV float3 nee_resolve_pair(int ds, const NeeRay& qb, const NeeRay& ql, ShadeCounts* counts)
+{
+    float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
+    if (qb.active)
+    {
+        float t;
+        const int s = scene_closest(qb.ray, &t);
+        Lb = nee_bsdf_resolve(qb, s, t);
+        counts->traced++;
+    }
+    if (ql.active)
+    {
+        Ll = scene_any_hit(ql.ray) ? KYD_BLACK : ql.value;
+        counts->traced++;
+    }
+    if (ds == KYD_DS_BOTH_MIS)
+        return add(mul(Lb, 0.5f), mul(Ll, 0.5f));
+    return (ds == KYD_DS_BSDF || ds == KYD_DS_BSDF_MIS) ? Lb : Ll;
+}
 
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
 // HOT: the headline configuration (path_tracing_iteration_t, both_mis, LCG48 sampler, light-sample inside shade)
 // with those run-time switches compiled out; !HOT reads them from the parameters
 template <int LOBE, int TRAITS, bool HOT>
 KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee,
-                          ShadeCounts* counts)
+                          ShadeCounts* counts, float4 rec0, float4 rec1, float4 rec2, float4 rec3)
 {
     const int ds = HOT ? (int)KYD_DS_BOTH_MIS : wp.rp.direct_sample;
     const bool direct_only = HOT ? false : wp.direct_only != 0;
@@ -382,7 +405,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     const bool debug_sampler = HOT ? false : wp.rp.sampler == KYD_SAMPLER_DEBUG;
     float4* p = path_line(w, slot);
     PathState st;
-    unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
+    unpack_path(st, rec0, rec1, rec2, rec3);
     Ray r;
     r.o = st.o;
     r.d = st.d;
@@ -446,13 +469,21 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                     const bool finite_beta = isfinite(beta.x) && isfinite(beta.y) && isfinite(beta.z);
                     if (qb.active || ql.active || !finite_beta)
                     {
-                        qb.ref_query = ql.ref_query = false; // counted here
-                        store_nee_line(nee_line(w, wp.plane, 0, slot), qb, ql, beta);
-                        new_pending = 1;
+                        // HOT: the vertex' two scene queries are traced right here (no light-sampling line, no shadow
+                        // stage, no deferred addition): L += beta * Ld as in ky.cpp:4575-4576
+                        if (HOT)
+                            Lo = add(Lo, cmulc(beta, add(KYD_BLACK, nee_resolve_pair(ds, qb, ql, counts))));
+                        else
+                        {
+                            qb.ref_query = ql.ref_query = false; // counted here
+                            store_nee_line(nee_line(w, wp.plane, 0, slot), qb, ql, beta);
+                            new_pending = 1;
+                        }
                     }
                 }
                 else if (TRAITS != TRAITS_AREA_RECTANGLE)
                 {
+                    // several lights: one line per (vertex, light); the shadow stage gives every query its own thread
                     Sampler ls = smp;
                     for (int l = 0; l < n_lights; ++l)
                     {
@@ -517,27 +548,58 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     int* const out_queues[2] = { next_queue, w.queue_nee[LOBE == LOBE_PHONG] };
     WarpPush<2> push;
     push.init();
-    ShadeCounts counts = { 0u };
+    ShadeCounts counts = { 0u, 0u };
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&counters->shade_vertices, (unsigned long long)n); // traffic model of bench.py
 
     // whole warps iterate together so that the ballots of the push are convergent; the queue entry is read one
     // iteration ahead
+    // the single-light kernels have the registers to load the next vertex' record while this one is shaded (its queue
+    // entry is then read two iterations ahead); the others would spill (profiles/r01_ab_variants.txt)
+    constexpr bool PREFETCH = HOT && TRAITS == TRAITS_AREA_RECTANGLE;
     long long ia = i;
     int slot_cur = ia < n ? queue[ia] : -1;
+    int slot_next = ia + stride < n ? queue[ia + stride] : -1;
+    float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0, rec2 = rec0, rec3 = rec0;
+    if (PREFETCH && slot_cur >= 0)
+    {
+        const float4* p0 = path_line(w, slot_cur);
+        rec0 = p0[P_ORIGIN]; rec1 = p0[P_DIRECTION]; rec2 = p0[P_BETA]; rec3 = p0[P_TAIL];
+    }
     for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, ia += stride)
     {
-        const int slot_next = ia + stride < n ? queue[ia + stride] : -1;
+        const long long i2 = ia + (PREFETCH ? 2ll : 1ll) * stride;
+        const int slot_ahead = i2 < n ? queue[i2] : -1;
+        float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0, nx2 = nx0, nx3 = nx0;
+        if (PREFETCH && slot_next >= 0)
+        {
+            const float4* pn = path_line(w, slot_next);
+            nx0 = pn[P_ORIGIN]; nx1 = pn[P_DIRECTION]; nx2 = pn[P_BETA]; nx3 = pn[P_TAIL];
+        }
         bool alive = false, wants_nee = false;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         if (slot_cur >= 0)
-            shade_vertex<LOBE, TRAITS, HOT>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &counts);
+        {
+            if (!PREFETCH)
+            {
+                const float4* p0 = path_line(w, slot);
+                rec0 = p0[P_ORIGIN]; rec1 = p0[P_DIRECTION]; rec2 = p0[P_BETA]; rec3 = p0[P_TAIL];
+            }
+            shade_vertex<LOBE, TRAITS, HOT>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &counts, rec0, rec1, rec2, rec3);
+        }
         push.commit(out_queues);
         push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
-        slot_cur = slot_next;
+        if (PREFETCH)
+        {
+            slot_cur = slot_next;
+            slot_next = slot_ahead;
+            rec0 = nx0; rec1 = nx1; rec2 = nx2; rec3 = nx3;
+        }
+        else
+            slot_cur = slot_ahead;
     }
     push.commit(out_queues);
-    flush_counters(counts.ref_rays, 0u, counters);
+    flush_counters(counts.ref_rays, counts.traced, counters);
 }
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which

@@ -4,15 +4,18 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 variants = {
     "base": [],
-    "traits1": ["-DKYD_TRAITS=1"],
-    "traits1_inline": ["-DKYD_TRAITS=1", "-DKYD_MATH_INLINE=1"],
+    "inshadow": ["-DKYD_INLINE_SHADOW=1"],
+    "inshadow_mb3": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_MIN_BLOCKS=3"],
+    "inshadow_pf": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_PREFETCH=1"],
+    "inshadow_pf_mb3": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_PREFETCH=1", "-DKYD_SHADE_MIN_BLOCKS=3"],
+    "pf": ["-DKYD_SHADE_PREFETCH=1"],
 }
 names = sys.argv[1:] or list(variants)
 os.makedirs(os.path.join(g.LIB, "ab"), exist_ok=True)
 procs = []
 for n in names:
     out = os.path.join(g.LIB, "ab", f"libkyd_{n}.so")
-    cmd = ["nvcc"] + g.NVCC_FLAGS + variants[n] + ["-shared", "-o", out, os.path.join(g.CSRC, "kyd_kernels.cu"), os.path.join(g.CSRC, "kyd_api.cu")]
-    procs.append((n, subprocess.Popen(cmd, cwd=g.ROOT)))
+    cmd = ["nvcc"] + g.NVCC_FLAGS + variants[n] + ["-shared", "-o", out, os.path.join(g.CSRC, "kyd_kernels.cu"), os.path.join(g.CSRC, "kyd_api.cu"), os.path.join(g.CSRC, "kyd_film.cu"), "-Xptxas", "-v"]
+    procs.append((n, subprocess.Popen(cmd, cwd=g.ROOT, stderr=open(os.path.join(g.LIB, "ab", f"{n}.ptxas.log"), "w"))))
 for n, p in procs:
     print(n, "rc", p.wait())
