@@ -12,10 +12,10 @@
 // lobe.  Shade runs once per lobe with lobe-specialised code, so a warp never mixes lobes.  Paths that miss
 // the scene are finished inside intersect.
 //
-// Data layout.  Lobe-sorted queues turn the state accesses into gathers over gigabytes, and the shade stage
-// is bound by scattered-DRAM throughput: it moved ~2.4 TB/s whether it wrote light-sampling records (352 B
-// per vertex, 103 ms per step) or not (224 B, 64.5 ms) -- profiles/r01_ab_variants.txt.  So the records are
-// as small as whole 32-byte sectors allow:
+// Data layout.  Lobe-sorted queues turn the state accesses into gathers over gigabytes; with 128-byte records the
+// shade stage was bound by scattered-DRAM throughput (~2.4 TB/s whether it wrote light-sampling records, 352 B per
+// vertex, 103 ms per step, or not, 224 B, 64.5 ms -- profiles/r01_ab_variants.txt).  So the records are as small
+// as whole 32-byte sectors allow:
 //   path line, 64 bytes:
 //     sector 0   origin.xyz, hit distance | direction.xyz, flags (previous vertex specular, pending light
 //                count, hit surface)                         intersect reads and rewrites it, shade rewrites it
@@ -29,9 +29,15 @@
 //   A vertex none of whose queries can contribute writes no light-sampling line and is not queued for shadow.
 //
 // Order of FP32 additions into a path's radiance Lo is the reference's: emitted light of a vertex, then
-// beta * Ld of that vertex (ky.cpp:4553-4576).  The Ld of a vertex becomes known one stage later than the
-// vertex is shaded, so it is added ("pending") at the start of the path's next shade (or when the path
-// misses, or by the accumulate kernel if the path ended) -- before anything else is added in every case.
+// beta * Ld of that vertex (ky.cpp:4553-4576).  Two ways to get Ld:
+//   - several lights (or a non-headline configuration): one light-sampling line per (vertex, light), resolved by the
+//     shadow stage with one thread per line.  Ld becomes known one stage later than the vertex is shaded, so it
+//     is added ("pending") at the start of the path's next shade (or when the path misses, or by the accumulate
+//     kernel if the path ended) -- before anything else is added in every case.
+//   - one light in the headline configuration (HOT kernels): the vertex' two scene queries are traced inside
+//     shade and Ld is added on the spot; no line, no shadow stage, no pending state (profiles/r01_ab_variants.txt:
+//     same shade + shadow time for Cornell, but the line traffic and the accumulate/miss re-reads go away; with
+//     five lights the per-line threads of the shadow stage win, so Veach keeps the deferred form).
 #pragma once
 
 #include "kyd_device.cuh"
