@@ -300,6 +300,27 @@ int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
         d.surf_material[i] = s.material;
         d.surf_light[i] = s.area_light;
     }
+    {
+        // traversal copy grouped by kind; list order inside a group (ties are resolved by surface index, see scene_closest)
+        const int group_kind[4] = { KYD_SHAPE_RECTANGLE, KYD_SHAPE_SPHERE, KYD_SHAPE_TRIANGLE, KYD_SHAPE_DISK };
+        int k = 0;
+        for (int g = 0; g < 4; ++g)
+        {
+            for (int i = 0; i < sc->surface_count; ++i)
+                if (d.surf_shape[i].kind == group_kind[g])
+                {
+                    d.sorted_shape[k] = d.surf_shape[i];
+                    d.sorted_surface[k] = i;
+                    ++k;
+                }
+            d.kind_end[g] = k;
+        }
+        for (int l = 0; l < KYD_MAX_LIGHTS; ++l)
+            d.light_surface[l] = -1;
+        for (int i = 0; i < sc->surface_count; ++i)
+            if (d.surf_light[i] >= 0)
+                d.light_surface[d.surf_light[i]] = d.light_surface[d.surf_light[i]] == -1 ? i : -2;
+    }
     for (int i = 0; i < sc->material_count; ++i)
     {
         const kyd_material& m = sc->materials[i];
@@ -329,6 +350,16 @@ int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
             d.light_shape[i] = convert_shape(sc->shapes[l.shape]);
         }
         if (l.kind == KYD_LIGHT_AREA || l.kind == KYD_LIGHT_ENVIRONMENT) d.n_nondelta_lights++;
+    }
+    // Where the occlusion form pays (A/B in profiles/r01_ab_variants.txt): sphere area lights, whose pdf_Li is positive
+    // for every direction (ky.cpp:1509-1512) so that every BSDF-sampled query would otherwise be traced, in scenes with
+    // several lights, where each traced query also costs a sector of a light-sampling line.  Elsewhere (one light:
+    // queries are traced inside shade; rectangle lights: pdf_Li already tests the hit) the closest-hit form is as fast.
+    for (int l = 0; l < KYD_MAX_LIGHTS; ++l)
+    {
+        const bool sphere_area = l < sc->light_count && sc->lights[l].kind == KYD_LIGHT_AREA && d.light_shape[l].kind == KYD_SHAPE_SPHERE;
+        if (!(sphere_area && sc->light_count > 1))
+            d.light_surface[l] = -2;
     }
     ctx->has_scene = true;
     ctx->scene_generation++;

@@ -761,35 +761,205 @@ KYD_DEV void material_scattering(const DevMaterial& m, const HitGeom& g, Bsdf* b
 
 // ---- scene traversal ky.cpp:3077-3088, 3172-3206 ------------------------------------------------------------
 
-// closest hit over all surfaces in list order (strict t < tmax keeps the first of equal distances)
+// The distance at which shape_t::intersect would report a hit if tmax were unbounded: the same arithmetic and the
+// same `distance > epsilon` test as shape_hit_distance_kind(), with `distance < ray.distance()` left to the caller.
+// (Sphere: the far root is tried only when the near one is not beyond epsilon; a near root rejected by tmax implies
+// the far one is rejected too, so picking the candidate first is equivalent to ky.cpp:1375-1383.)
+template <int KIND>
+KYD_DEV bool shape_hit_candidate(const DevShape& s, const Ray& r, float* out_t)
+{
+    if (KIND == KYD_SHAPE_SPHERE)
+    {
+        float3 oc = sub(s.p0, r.o);
+        float neg_b = dot(oc, r.d);
+        float discr = neg_b * neg_b - dot(oc, oc) + s.radius_sq;
+        if (!(discr >= 0))
+            return false;
+        float sqrt_discr = __fsqrt_rn(discr);
+        float t = neg_b - sqrt_discr;
+        if (!(t > KYD_SHAPE_EPSILON))
+            t = neg_b + sqrt_discr;
+        *out_t = t;
+        return t > KYD_SHAPE_EPSILON;
+    }
+    else if (KIND == KYD_SHAPE_RECTANGLE)
+    {
+        float3 oa = sub(s.p0, r.o), ob = sub(s.p1, r.o), oc = sub(s.p2, r.o), od = sub(s.p3, r.o);
+        float v0d = dot(cross(oc, ob), r.d);
+        float v1d = dot(cross(ob, oa), r.d);
+        float v2d = dot(cross(oa, od), r.d);
+        float v3d = dot(cross(od, oc), r.d);
+        if (!(((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f) && (v3d < 0.f)) ||
+              ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f) && (v3d >= 0.f))))
+            return false;
+        float t = dot(s.n, oa) / dot(s.n, r.d);
+        *out_t = t;
+        return t > KYD_SHAPE_EPSILON;
+    }
+    else if (KIND == KYD_SHAPE_TRIANGLE)
+    {
+        float3 oa = sub(s.p0, r.o), ob = sub(s.p1, r.o), oc = sub(s.p2, r.o);
+        float v0d = dot(cross(oc, ob), r.d);
+        float v1d = dot(cross(ob, oa), r.d);
+        float v2d = dot(cross(oa, oc), r.d);
+        if (!(((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f)) || ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f))))
+            return false;
+        float t = dot(s.n, oa) / dot(s.n, r.d);
+        *out_t = t;
+        return t > KYD_SHAPE_EPSILON;
+    }
+    else
+    {
+        if (is_equal0(dot(r.d, s.n)))
+            return false;
+        float3 op = sub(s.p0, r.o);
+        float t = dot(s.n, op) / dot(s.n, r.d);
+        *out_t = t;
+        if (!(t > KYD_SHAPE_EPSILON))
+            return false;
+        return distance(s.p0, ray_at(r, t)) <= s.radius;
+    }
+}
+
+// One loop per shape kind over the kind-sorted copy of the surface list: no per-surface dispatch, and the loop
+// counter, the bounds and the shape data stay warp-uniform (uniform-datapath constant loads).  The reference walks
+// the list in order with a strict `t < tmax` (ky.cpp:3172-3184), i.e. the closest hit, the LOWEST surface index among
+// equal distances; visiting in another order needs that tie rule spelled out.
+template <int GROUP, int KIND>
+KYD_DEV void scene_closest_kind(const Ray& r, float& tmax, int& best)
+{
+    const int end = c_scene.kind_end[GROUP];
+    for (int k = GROUP == 0 ? 0 : c_scene.kind_end[GROUP == 0 ? 0 : GROUP - 1]; k < end; ++k)
+    {
+        float t;
+        if (shape_hit_candidate<KIND>(c_scene.sorted_shape[k], r, &t))
+        {
+            const int surface = c_scene.sorted_surface[k];
+            if (t < tmax || (t == tmax && surface < best))
+            {
+                tmax = t;
+                best = surface;
+            }
+        }
+    }
+}
+
 KYD_DEV int scene_closest(const Ray& r, float* out_t)
 {
     float tmax = r.tmax;
     int best = -1;
-    const int n = c_scene.n_surfaces;
-    for (int i = 0; i < n; ++i)
-    {
-        float t;
-        if (shape_hit_distance(c_scene.surf_shape[i], r, tmax, &t))
-        {
-            tmax = t;
-            best = i;
-        }
-    }
+    scene_closest_kind<0, KYD_SHAPE_RECTANGLE>(r, tmax, best);
+    scene_closest_kind<1, KYD_SHAPE_SPHERE>(r, tmax, best);
+    scene_closest_kind<2, KYD_SHAPE_TRIANGLE>(r, tmax, best);
+    scene_closest_kind<3, KYD_SHAPE_DISK>(r, tmax, best);
     *out_t = tmax;
     return best;
 }
 
-KYD_DEV bool scene_any_hit(const Ray& r)
+template <int GROUP, int KIND>
+KYD_DEV bool scene_any_hit_kind(const Ray& r)
 {
-    const int n = c_scene.n_surfaces;
-    for (int i = 0; i < n; ++i)
+    const int end = c_scene.kind_end[GROUP];
+    for (int k = GROUP == 0 ? 0 : c_scene.kind_end[GROUP == 0 ? 0 : GROUP - 1]; k < end; ++k)
     {
         float t;
-        if (shape_hit_distance(c_scene.surf_shape[i], r, r.tmax, &t))
+        if (shape_hit_candidate<KIND>(c_scene.sorted_shape[k], r, &t) && t < r.tmax)
             return true;
     }
     return false;
+}
+
+// scene_t::occluded's question (ky.cpp:3187-3206): is any surface hit inside (epsilon, tmax)?  Order-independent.
+KYD_DEV bool scene_any_hit(const Ray& r)
+{
+    return scene_any_hit_kind<0, KYD_SHAPE_RECTANGLE>(r) || scene_any_hit_kind<1, KYD_SHAPE_SPHERE>(r) ||
+           scene_any_hit_kind<2, KYD_SHAPE_TRIANGLE>(r) || scene_any_hit_kind<3, KYD_SHAPE_DISK>(r);
+}
+
+// Occlusion form of the BSDF-sampled query: is any surface other than `light_surface` hit before it?  "Before" is the
+// list-order closest-hit rule: a smaller distance, or the same distance and a lower surface index.  r.tmax = the distance
+// of light_surface along r.
+template <int GROUP, int KIND>
+KYD_DEV bool scene_blocked_before_kind(const Ray& r, int light_surface)
+{
+    const int end = c_scene.kind_end[GROUP];
+    for (int k = GROUP == 0 ? 0 : c_scene.kind_end[GROUP == 0 ? 0 : GROUP - 1]; k < end; ++k)
+    {
+        float t;
+        if (shape_hit_candidate<KIND>(c_scene.sorted_shape[k], r, &t))
+        {
+            const int surface = c_scene.sorted_surface[k];
+            if (surface != light_surface && (t < r.tmax || (t == r.tmax && surface < light_surface)))
+                return true;
+        }
+    }
+    return false;
+}
+
+KYD_DEV bool scene_blocked_before(const Ray& r, int light_surface)
+{
+    return scene_blocked_before_kind<0, KYD_SHAPE_RECTANGLE>(r, light_surface) || scene_blocked_before_kind<1, KYD_SHAPE_SPHERE>(r, light_surface) ||
+           scene_blocked_before_kind<2, KYD_SHAPE_TRIANGLE>(r, light_surface) || scene_blocked_before_kind<3, KYD_SHAPE_DISK>(r, light_surface);
+}
+
+// warp-uniform form (every lane calls it; lanes without a query pass light_surface < 0)
+template <int GROUP, int KIND>
+KYD_DEV bool scene_blocked_before_kind_uniform(const Ray& r, int light_surface, bool done)
+{
+    const int end = c_scene.kind_end[GROUP];
+    for (int k = GROUP == 0 ? 0 : c_scene.kind_end[GROUP == 0 ? 0 : GROUP - 1]; k < end; ++k)
+    {
+        float t;
+        if (shape_hit_candidate<KIND>(c_scene.sorted_shape[k], r, &t))
+        {
+            const int surface = c_scene.sorted_surface[k];
+            if (surface != light_surface && (t < r.tmax || (t == r.tmax && surface < light_surface)))
+                done = true;
+        }
+    }
+    return done;
+}
+
+KYD_DEV bool scene_blocked_before_uniform(const Ray& r, int light_surface)
+{
+    const bool idle = light_surface < 0;
+    bool done = idle;
+    done = scene_blocked_before_kind_uniform<0, KYD_SHAPE_RECTANGLE>(r, light_surface, done);
+    if (__all_sync(0xffffffffu, done)) return !idle;
+    done = scene_blocked_before_kind_uniform<1, KYD_SHAPE_SPHERE>(r, light_surface, done);
+    if (__all_sync(0xffffffffu, done)) return !idle;
+    done = scene_blocked_before_kind_uniform<2, KYD_SHAPE_TRIANGLE>(r, light_surface, done);
+    done = scene_blocked_before_kind_uniform<3, KYD_SHAPE_DISK>(r, light_surface, done);
+    return done && !idle;
+}
+
+// The same question asked by all 32 lanes of a warp together (lanes without a query pass tmax < 0): no per-lane early
+// exit -- in SIMT it saves nothing while any lane is still looking -- so the loops stay warp-uniform; the warp leaves
+// between kind groups once every lane has its answer.
+template <int GROUP, int KIND>
+KYD_DEV bool scene_any_hit_kind_uniform(const Ray& r, bool hit)
+{
+    const int end = c_scene.kind_end[GROUP];
+    for (int k = GROUP == 0 ? 0 : c_scene.kind_end[GROUP == 0 ? 0 : GROUP - 1]; k < end; ++k)
+    {
+        float t;
+        if (shape_hit_candidate<KIND>(c_scene.sorted_shape[k], r, &t) && t < r.tmax)
+            hit = true;
+    }
+    return hit;
+}
+
+KYD_DEV bool scene_any_hit_uniform(const Ray& r)
+{
+    bool hit = !(r.tmax > KYD_SHAPE_EPSILON);   // nothing lies in (epsilon, tmax): answered (the caller ignores it)
+    if (__all_sync(0xffffffffu, hit)) return false;
+    hit = scene_any_hit_kind_uniform<0, KYD_SHAPE_RECTANGLE>(r, hit);
+    if (__all_sync(0xffffffffu, hit)) return r.tmax > KYD_SHAPE_EPSILON;
+    hit = scene_any_hit_kind_uniform<1, KYD_SHAPE_SPHERE>(r, hit);
+    if (__all_sync(0xffffffffu, hit)) return r.tmax > KYD_SHAPE_EPSILON;
+    hit = scene_any_hit_kind_uniform<2, KYD_SHAPE_TRIANGLE>(r, hit);
+    hit = scene_any_hit_kind_uniform<3, KYD_SHAPE_DISK>(r, hit);
+    return hit && r.tmax > KYD_SHAPE_EPSILON;
 }
 
 KYD_DEV float3 areal_radiance(const DevLight& l, float3 light_normal, float3 wo) // ky.cpp:2957-2960
@@ -909,6 +1079,9 @@ struct NeeRay
     Ray ray;        // tmax = inf: closest-hit query (BSDF-sampled); finite: occlusion query (light-sampled)
     float3 value;   // contribution if the query succeeds
     int light;      // closest-hit query: the light the hit surface must carry (or be missed for the environment light)
+    int light_surface; // >= 0: the BSDF-sampled query in its occlusion form -- ray.tmax is the distance at which the ray
+                    // hits this surface (the only one carrying the light, lit side) and the query succeeds unless another
+                    // surface comes first (scene_blocked_before)
     bool active;    // the query can change the result and has to be traced
     bool ref_query; // the reference issues this scene query (it traces before it knows the result is black)
 };
@@ -922,6 +1095,7 @@ KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, 
     q.active = false;
     q.ref_query = false;
     q.light = light_index;
+    q.light_surface = -1;
     q.value = KYD_BLACK;
     const DevLight& l = c_scene.lights[light_index];
     if (bsdf_is_delta(b.lobe) || light_is_delta(light_kind<TRAITS>(l)))
@@ -936,6 +1110,25 @@ KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, 
     float3 Li = l.color;
     if (is_black(Li))
         return q;
+    // The reference traces the ray and then asks whether the closest hit carries this light (ky.cpp:3905-3919,
+    // 3987-4001).  "The closest hit is surface s" == "s is hit, and no other surface is hit before it": the first half
+    // needs one shape test and settles most queries right here (a sphere light's pdf_Li is positive for EVERY direction,
+    // ky.cpp:1509-1512, so without this each of them costs a full traversal); the second half is an occlusion query.
+    // (upload enables this per light where it pays, kyd_api.cu; never for the single rectangle light of TRAITS_AREA_RECTANGLE)
+    const int ls = TRAITS == TRAITS_AREA_RECTANGLE ? -2 : c_scene.light_surface[light_index];
+    if (light_kind<TRAITS>(l) == KYD_LIGHT_AREA && ls != -2)
+    {
+        if (ls < 0)
+            return q;   // no surface carries the light: whatever the ray hits, it is not this light
+        float t_light;
+        if (!shape_hit_distance(c_scene.surf_shape[ls], q.ray, KYD_INF, &t_light))
+            return q;
+        HitGeom lg = shape_hit_geom(c_scene.surf_shape[ls], q.ray, t_light);
+        if (!(dot(lg.normal, lg.wo) > 0))
+            return q;   // areal_radiance is one-sided (ky.cpp:2957-2960)
+        q.light_surface = ls;
+        q.ray.tmax = t_light;
+    }
     if (!mis)
         q.value = cdiv(cmulc(f_cos, Li), bs.pdf);
     else
@@ -964,6 +1157,16 @@ KYD_DEV float3 nee_bsdf_resolve(const NeeRay& q, int hit_surface, float hit_t)
     return l.kind == KYD_LIGHT_ENVIRONMENT ? q.value : KYD_BLACK;
 }
 
+// traces an active BSDF-sampled query in whichever form nee_bsdf_setup left it
+KYD_DEV float3 nee_bsdf_trace(const NeeRay& q)
+{
+    if (q.light_surface >= 0)
+        return scene_blocked_before(q.ray, q.light_surface) ? KYD_BLACK : q.value;
+    float t;
+    const int s = scene_closest(q.ray, &t);
+    return nee_bsdf_resolve(q, s, t);
+}
+
 // light-sampled half: estimate_direct_lighting_by_emitter (ky.cpp:3933-3962) when mis == false,
 // estimate_direct_lighting_by_emitter_mis (ky.cpp:4035-4074) when mis == true
 template <int TRAITS = TRAITS_ANY>
@@ -973,6 +1176,7 @@ KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index,
     q.active = false;
     q.ref_query = false;
     q.light = light_index;
+    q.light_surface = -1;
     q.value = KYD_BLACK;
     const DevLight& l = c_scene.lights[light_index];
     if (bsdf_is_delta(b.lobe))

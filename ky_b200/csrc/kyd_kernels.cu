@@ -61,11 +61,7 @@ KYD_DEV float3 nee_trace(const NeeRay& q, bool closest, Counters& c)
         return KYD_BLACK;
     c.traced++;
     if (closest)
-    {
-        float t;
-        int s = scene_closest(q.ray, &t);
-        return nee_bsdf_resolve(q, s, t);
-    }
+        return nee_bsdf_trace(q);
     return scene_any_hit(q.ray) ? KYD_BLACK : q.value;
 }
 

@@ -54,6 +54,13 @@ struct DevScene
     DevMaterial materials[KYD_MAX_MATERIALS];
     DevLight lights[KYD_MAX_LIGHTS];
     DevShape light_shape[KYD_MAX_LIGHTS];   // area_light_t::shape_, independent of the surface list
+    // traversal copy of the surfaces' geometry grouped by shape kind (rectangle, sphere, triangle, disk), list order
+    // kept inside a group: one branch-free loop per kind whose loads are warp-uniform (kyd_device.cuh, scene_closest)
+    int light_surface[KYD_MAX_LIGHTS];      // occlusion form of the BSDF-sampled query (nee_bsdf_setup): the one surface whose
+                                            // area_light is light l; -1: none carries it; -2: form not used for this light
+    DevShape sorted_shape[KYD_MAX_SURFACES];
+    int sorted_surface[KYD_MAX_SURFACES];   // surface index of sorted_shape[k]
+    int kind_end[4];                        // sorted_shape[kind_end[g-1] .. kind_end[g]) is group g
 };
 
 struct RenderParams

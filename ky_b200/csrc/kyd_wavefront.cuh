@@ -61,7 +61,8 @@ enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_BETA = 
 // flags word of a path (w of the direction unit)
 enum { FLAG_PREV_SPECULAR = 1, FLAG_PENDING_SHIFT = 4, FLAG_PENDING_MASK = 0x1f << 4, FLAG_SURFACE_SHIFT = 12 };
 // flags word of a light-sampling line (w of the light query's direction unit)
-enum { NEE_REF_BSDF = 1, NEE_REF_LIGHT = 2, NEE_BSDF_LIVE = 4 };
+// (bits 8..: 1 + the light's surface when the BSDF-sampled query is in its occlusion form, NeeRay::light_surface)
+enum { NEE_REF_BSDF = 1, NEE_REF_LIGHT = 2, NEE_BSDF_LIVE = 4, NEE_LIGHT_SURFACE_SHIFT = 8 };
 
 struct WaveParams
 {
@@ -268,7 +269,8 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
         o = p0[P_ORIGIN];
         d = p0[P_DIRECTION];
     }
-    for (int i0 = base_i - (threadIdx.x & 31); i0 < n; i0 += stride, ia += stride)
+    // block-uniform trip count (the tail costs at most one idle iteration per warp): keeps the loop itself uniform
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride, ia += stride)
     {
         int lobe = -1;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
@@ -281,16 +283,18 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
             o_next = pn[P_ORIGIN];
             d_next = pn[P_DIRECTION];
         }
+        // the traversal runs for the whole warp, outside any divergent branch (idle lanes trace a null ray that hits
+        // nothing): its loop counters and shape loads then stay in the uniform datapath
+        Ray r;
+        r.o = V3(o.x, o.y, o.z);
+        r.d = V3(d.x, d.y, d.z);
+        r.tmax = slot_cur >= 0 ? KYD_INF : -1.f; // extension rays are unbounded (ky.cpp:585, 665-668)
+        float t;
+        const int s = scene_closest(r, &t);
         if (slot_cur >= 0)
         {
             float4* p = path_line(w, slot);
-            Ray r;
-            r.o = V3(o.x, o.y, o.z);
-            r.d = V3(d.x, d.y, d.z);
-            r.tmax = KYD_INF; // extension rays are unbounded (ky.cpp:585, 665-668)
             const int flags = __float_as_int(d.w);
-            float t;
-            const int s = scene_closest(r, &t);
             rays++;
             if (s >= 0)
             {
@@ -344,6 +348,7 @@ KYD_DEV void light_sample_pair(int ds, const HitGeom& g, const Bsdf& b, int l, S
     qb->ray.o = qb->ray.d = ql->ray.o = ql->ray.d = V3(0, 0, 0);
     qb->ray.tmax = ql->ray.tmax = -1.f;
     qb->light = ql->light = l;
+    qb->light_surface = ql->light_surface = -1;
     if (ds == KYD_DS_BSDF)
     {
         if (!light_is_delta(light_kind<TRAITS>(c_scene.lights[l])))
@@ -360,7 +365,8 @@ KYD_DEV void light_sample_pair(int ds, const HitGeom& g, const Bsdf& b, int l, S
 // writes the light-sampling line of (light, path): sectors 0-1 always, sector 2 only for a live BSDF-sampled query
 KYD_DEV void store_nee_line(float4* line, const NeeRay& qb, const NeeRay& ql, float3 vertex_beta)
 {
-    const int flags = (qb.ref_query ? NEE_REF_BSDF : 0) | (ql.ref_query ? NEE_REF_LIGHT : 0) | (qb.active ? NEE_BSDF_LIVE : 0);
+    const int flags = (qb.ref_query ? NEE_REF_BSDF : 0) | (ql.ref_query ? NEE_REF_LIGHT : 0) | (qb.active ? NEE_BSDF_LIVE : 0) |
+                      ((qb.light_surface + 1) << NEE_LIGHT_SURFACE_SHIFT);
     line[N_LIGHT_O] = make_float4(ql.ray.o.x, ql.ray.o.y, ql.ray.o.z, ql.active ? ql.ray.tmax : -1.f); // tmax < 0: no query
     line[N_LIGHT_D] = make_float4(ql.ray.d.x, ql.ray.d.y, ql.ray.d.z, __int_as_float(flags));
     line[N_LIGHT_VALUE] = make_float4(ql.value.x, ql.value.y, ql.value.z, vertex_beta.x);
@@ -383,9 +389,7 @@ KYD_DEV float3 nee_resolve_pair(int ds, const NeeRay& qb, const NeeRay& ql, Shad
     float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
     if (qb.active)
     {
-        float t;
-        const int s = scene_closest(qb.ray, &t);
-        Lb = nee_bsdf_resolve(qb, s, t);
+        Lb = nee_bsdf_trace(qb);
         counts->traced++;
     }
     if (ql.active)
@@ -572,7 +576,7 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
         const float4* p0 = path_line(w, slot_cur);
         rec0 = p0[P_ORIGIN]; rec1 = p0[P_DIRECTION]; rec2 = p0[P_BETA]; rec3 = p0[P_TAIL];
     }
-    for (int i0 = i - (threadIdx.x & 31); i0 < n; i0 += stride, ia += stride)
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride, ia += stride) // block-uniform trip count
     {
         const long long i2 = ia + (PREFETCH ? 2ll : 1ll) * stride;
         const int slot_ahead = i2 < n ? queue[i2] : -1;
@@ -675,38 +679,72 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
             atomicAdd(&counters->shade_lines, (unsigned long long)n * n_lights); // lines shade wrote for this stage
         const int* __restrict__ nee_queue = w.queue_nee[c];
         const long long total = (long long)n * n_lights;
-        for (long long idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+        // block-uniform trip count and traversals outside divergent branches (idle lanes trace null rays): the
+        // traversal loops stay in the uniform datapath, as in k_intersect
+        for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride)
         {
-            const int l = (int)(idx / n);
-            const int slot = nee_queue[idx - (long long)l * n];
+            const long long idx = base + threadIdx.x;
+            const bool valid = idx < total;
+            const int l = valid ? (int)(idx / n) : 0;
+            const int slot = valid ? nee_queue[idx - (long long)l * n] : 0;
             float4* line = nee_line(w, wp.plane, l, slot);
-            const float4 lo = line[N_LIGHT_O], ld = line[N_LIGHT_D], lv = line[N_LIGHT_VALUE], mx = line[N_MIXED];
+            float4 lo = make_float4(0.f, 0.f, 0.f, -1.f), ld = make_float4(0.f, 0.f, 0.f, 0.f), lv = ld, mx = ld;
+            if (valid)
+            {
+                lo = line[N_LIGHT_O]; ld = line[N_LIGHT_D]; lv = line[N_LIGHT_VALUE]; mx = line[N_MIXED];
+            }
             const int flags = __float_as_int(ld.w);
             rays += (unsigned)((flags & NEE_REF_BSDF) != 0) + (unsigned)((flags & NEE_REF_LIGHT) != 0);
 
             float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
-            if (flags & NEE_BSDF_LIVE)
+            const bool live = (flags & NEE_BSDF_LIVE) != 0;
+            if (__any_sync(0xffffffffu, live))
             {
-                const float4 bo = line[N_BSDF_O], bd = line[N_BSDF_D];
                 NeeRay q;
-                q.ray.o = V3(bo.x, bo.y, bo.z);
-                q.ray.d = V3(bd.x, bd.y, bd.z);
-                q.ray.tmax = bo.w;
-                q.value = V3(mx.z, mx.w, bd.w);
+                q.ray.o = q.ray.d = V3(0.f, 0.f, 0.f);
+                q.ray.tmax = -1.f;
+                q.value = KYD_BLACK;
                 q.light = l;
-                float t;
-                int s = scene_closest(q.ray, &t);
-                Lb = nee_bsdf_resolve(q, s, t);
-                traced++;
+                q.light_surface = -1;
+                if (live)
+                {
+                    const float4 bo = line[N_BSDF_O], bd = line[N_BSDF_D];
+                    q.ray.o = V3(bo.x, bo.y, bo.z);
+                    q.ray.d = V3(bd.x, bd.y, bd.z);
+                    q.ray.tmax = bo.w;
+                    q.value = V3(mx.z, mx.w, bd.w);
+                    q.light_surface = (flags >> NEE_LIGHT_SURFACE_SHIFT) - 1;
+                }
+                const bool occlusion_form = live && q.light_surface >= 0;
+                if (__any_sync(0xffffffffu, occlusion_form))
+                {
+                    const bool blocked = scene_blocked_before_uniform(q.ray, occlusion_form ? q.light_surface : -1);
+                    if (occlusion_form)
+                        Lb = blocked ? KYD_BLACK : q.value;
+                }
+                if (__any_sync(0xffffffffu, live && !occlusion_form))
+                {
+                    Ray r = q.ray;
+                    if (occlusion_form) r.tmax = -1.f;
+                    float t;
+                    const int s = scene_closest(r, &t);
+                    if (live && !occlusion_form)
+                        Lb = nee_bsdf_resolve(q, s, t);
+                }
+                if (live)
+                    traced++;
             }
-            if (lo.w >= 0.f)
             {
                 Ray r;
                 r.o = V3(lo.x, lo.y, lo.z);
                 r.d = V3(ld.x, ld.y, ld.z);
-                r.tmax = lo.w;
-                Ll = scene_any_hit(r) ? KYD_BLACK : V3(lv.x, lv.y, lv.z);
-                traced++;
+                r.tmax = lo.w;                    // < 0: no query, nothing can be hit
+                const bool occluded = scene_any_hit_uniform(r);
+                if (lo.w >= 0.f)
+                {
+                    Ll = occluded ? KYD_BLACK : V3(lv.x, lv.y, lv.z);
+                    traced++;
+                }
             }
             float3 e;
             if (ds == KYD_DS_BOTH_MIS)
@@ -715,8 +753,11 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
                 e = Lb;
             else
                 e = Ll;
-            line[N_RESULT] = make_float4(e.x, e.y, e.z, 0.f);
-            line[N_VERTEX_BETA] = make_float4(lv.w, mx.x, mx.y, 0.f);
+            if (valid)
+            {
+                line[N_RESULT] = make_float4(e.x, e.y, e.z, 0.f);
+                line[N_VERTEX_BETA] = make_float4(lv.w, mx.x, mx.y, 0.f);
+            }
         }
     }
     flush_counters(rays, traced, counters);

@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as g
 variants = {
     "base": [],
+    "cur": [],
     "inshadow": ["-DKYD_INLINE_SHADOW=1"],
     "inshadow_mb3": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_MIN_BLOCKS=3"],
     "inshadow_pf": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_PREFETCH=1"],

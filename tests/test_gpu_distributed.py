@@ -2,6 +2,7 @@
 import os
 import socket
 import sys
+import time
 
 import numpy as np
 import pytest
@@ -30,6 +31,8 @@ def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
+    for k in [k for k in os.environ if k.startswith("TORCHELASTIC") or k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "GROUP_RANK")]:
+        del os.environ[k]  # a launcher's environment must not leak into this private two-rank group
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -58,7 +61,13 @@ def test_two_gpu_split_reduce_clamp(tmp_path):
     port = s.getsockname()[1]
     s.close()
     out = str(tmp_path / "film.npy")
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    ctx = mp.spawn(_worker, args=(2, port, out), nprocs=2, join=False)
+    deadline = time.time() + 300
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for proc in ctx.processes:
+                proc.kill()
+            pytest.fail("two-rank NCCL job did not finish within 300 s")
     got = np.load(out)
     scene = ky.Scene(ky.SCENE_CORNELL, W, H)
     want, _ = kyo.render(scene, ky.render_desc(W, H, SPP))
