@@ -5,6 +5,7 @@ import __graft_entry__ as g
 variants = {
     "base": [],
     "cur": [],
+    "slowsincos": ["-DKYD_FAST_SINCOS=0"],
     "inshadow": ["-DKYD_INLINE_SHADOW=1"],
     "inshadow_mb3": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_MIN_BLOCKS=3"],
     "inshadow_pf": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_PREFETCH=1"],
