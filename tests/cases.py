@@ -69,3 +69,73 @@ def stage_film(width, height, seed, scale=False):
 # (name, width, height, seed, scale): odd sizes so that 3*w is not a multiple of 4 and words straddle bmp lines
 STAGE_FILMS = [("37x21", 37, 21, 1, False), ("37x21s", 37, 21, 2, True), ("1x1", 1, 1, 3, False), ("5x3", 5, 3, 4, True),
                ("64x48", 64, 48, 5, False), ("3x7", 3, 7, 6, True)]
+
+
+# ---- hand-assembled scenes (kyd_scene_desc built in Python) ------------------------------------------------------
+class CustomScene:
+    """A kyd_scene_desc assembled from ctypes arrays; quacks like ky_b200.Scene for Device.upload and kyo.render."""
+
+    def __init__(self, base, shapes, materials, lights, surfaces, environment_light=-1):
+        import ctypes as C
+        import ky_b200 as ky
+        self._keep = (base,
+                      (ky.Shape * len(shapes))(*shapes), (ky.Material * len(materials))(*materials),
+                      (ky.Light * max(1, len(lights)))(*lights), (ky.Surface * len(surfaces))(*surfaces))
+        d = ky.SceneDesc()
+        d.camera = base.desc.camera
+        d.shape_count, d.shapes = len(shapes), self._keep[1]
+        d.material_count, d.materials = len(materials), self._keep[2]
+        d.light_count, d.lights = len(lights), self._keep[3]
+        d.surface_count, d.surfaces = len(surfaces), self._keep[4]
+        d.environment_light = environment_light
+        self.desc = d
+        self.desc_ptr = C.pointer(d)
+        self.width, self.height = base.width, base.height
+
+
+def coplanar_tie_scene(order):
+    """Cornell box + a disk and a triangle lying exactly in the plane of the back wall (axis-aligned, so all three report
+    bit-identical hit distances where they overlap), each with its own matte colour.  order = "first": the two come
+    BEFORE the Cornell surfaces in the list (they must win the ties), "last": after (the wall must win).  The reference
+    resolves equal distances by list order (strict `t < tmax`, ky.cpp:3172-3184); the device visits surfaces grouped by
+    kind, so this pins its tie rule."""
+    import ky_b200 as ky
+    base = make_scene("cornell")
+    shapes, materials, lights, surfaces = base.shapes, base.materials, base.lights, base.surfaces
+    wall = None
+    for i, sf in enumerate(surfaces):
+        s = shapes[sf.shape]
+        zs = [s.p0[2], s.p1[2], s.p2[2], s.p3[2]]
+        if s.kind == ky.SHAPE_RECTANGLE and abs(s.normal[2]) == 1.0 and max(zs) == min(zs) and sf.area_light < 0:
+            if wall is None or zs[0] > shapes[surfaces[wall].shape].p0[2]:
+                wall = i
+    w = shapes[surfaces[wall].shape]
+    cx = (w.p0[0] + w.p1[0] + w.p2[0] + w.p3[0]) / 4
+    cy = (w.p0[1] + w.p1[1] + w.p2[1] + w.p3[1]) / 4
+    disk = ky.Shape()
+    disk.kind = ky.SHAPE_DISK
+    disk.p0[:] = [cx, cy, w.p0[2]]
+    disk.normal[:] = list(w.normal)
+    disk.radius, disk.radius_sq, disk.area = 160.0, 160.0 * 160.0, 3.14159274 * 160.0 * 160.0
+    tri = ky.Shape()
+    tri.kind = ky.SHAPE_TRIANGLE
+    tri.p0[:], tri.p1[:], tri.p2[:] = list(w.p0), list(w.p1), list(w.p2)
+    tri.normal[:] = list(w.normal)
+    tri.area = w.area / 2
+
+    def matte(r, g, b):
+        m = ky.Material()
+        m.kind = ky.MAT_MATTE
+        m.diffuse[:] = [r, g, b]
+        return m
+
+    n_s, n_m = len(shapes), len(materials)
+    shapes = shapes + [disk, tri]
+    materials = materials + [matte(0.9, 0.1, 0.1), matte(0.1, 0.9, 0.1)]
+    extra = []
+    for k in range(2):
+        sf = ky.Surface()
+        sf.shape, sf.material, sf.area_light = n_s + k, n_m + k, -1
+        extra.append(sf)
+    surfaces = extra + surfaces if order == "first" else surfaces + extra
+    return CustomScene(base, shapes, materials, lights, surfaces, base.desc.environment_light)

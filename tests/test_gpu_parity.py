@@ -92,6 +92,25 @@ def test_fast_pow_matches_its_definition(device):
     assert slow < 0.2 * (1 << 31)
 
 
+@pytest.mark.parametrize("order", ["first", "last"])
+@pytest.mark.parametrize("integrator,flags", [(ky.INT_BASECOLOR, 0), (ky.INT_PT_ITERATION, 0), (ky.INT_PT_ITERATION, ky.FLAG_FUSED),
+                                              (ky.INT_DIRECT_LIGHTING, 0)])
+def test_equal_hit_distances_resolve_in_list_order(device, order, integrator, flags):
+    """A disk and a triangle exactly in the plane of a Cornell wall: three shape kinds report bit-identical distances.  The
+    reference keeps the first surface in list order; the device walks surfaces grouped by kind and must still do so."""
+    scene = cases.coplanar_tie_scene(order)
+    desc = ky.render_desc(cases.W, cases.H, 4, integrator=integrator, max_depth=3, flags=flags)
+    device.upload(scene)
+    got = device.render(desc)
+    want, rays = kyo.render(scene, desc)
+    _assert_same(got, want, f"tie scene {order}")
+    assert device.stats().rays == rays
+    if integrator == ky.INT_BASECOLOR:
+        # the tie really happens and really matters: the two orders give different images
+        other = kyo.render(cases.coplanar_tie_scene("last" if order == "first" else "first"), desc)[0]
+        assert (_bits(other) != _bits(want)).any()
+
+
 def test_debug_sampler(device):
     scene = cases.make_scene("cornell")
     desc = ky.render_desc(cases.W, cases.H, 2, sampler=ky.SAMPLER_DEBUG)
