@@ -139,3 +139,20 @@ def coplanar_tie_scene(order):
         extra.append(sf)
     surfaces = extra + surfaces if order == "first" else surfaces + extra
     return CustomScene(base, shapes, materials, lights, surfaces, base.desc.environment_light)
+
+
+def light_tie_scene(order):
+    """Veach scene + a matte copy of the first sphere light's surface (same shape: bit-identical hit distances), listed
+    before ("first": the copy hides the light from every BSDF-sampled ray) or after ("last": the light wins) the others.
+    Pins the tie rule of the occlusion form of BSDF-sampled light queries (scene_blocked_before)."""
+    import ky_b200 as ky
+    base = make_scene("veach")
+    shapes, materials, lights, surfaces = base.shapes, base.materials, base.lights, base.surfaces
+    lit = next(i for i, sf in enumerate(surfaces) if sf.area_light >= 0 and shapes[sf.shape].kind == ky.SHAPE_SPHERE)
+    m = ky.Material()
+    m.kind = ky.MAT_MATTE
+    m.diffuse[:] = [0.2, 0.3, 0.9]
+    copy = ky.Surface()
+    copy.shape, copy.material, copy.area_light = surfaces[lit].shape, len(materials), -1
+    surfaces = [copy] + surfaces if order == "first" else surfaces + [copy]
+    return CustomScene(base, shapes, materials + [m], lights, surfaces, base.desc.environment_light)

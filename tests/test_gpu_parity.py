@@ -111,6 +111,20 @@ def test_equal_hit_distances_resolve_in_list_order(device, order, integrator, fl
         assert (_bits(other) != _bits(want)).any()
 
 
+@pytest.mark.parametrize("order", ["first", "last"])
+@pytest.mark.parametrize("ds,flags", [(ky.DS_BOTH_MIS, 0), (ky.DS_BSDF_MIS, 0), (ky.DS_BSDF, 0), (ky.DS_BOTH_MIS, ky.FLAG_FUSED)])
+def test_light_surface_tied_with_another_surface(device, order, ds, flags):
+    """A matte copy of a sphere light's surface: the BSDF-sampled query must see the light only if the light's surface
+    comes first in list order (the occlusion form of the query has its own tie rule)."""
+    scene = cases.light_tie_scene(order)
+    desc = ky.render_desc(cases.W, cases.H, 4, integrator=ky.INT_PT_ITERATION, max_depth=3, direct_sample=ds, flags=flags)
+    device.upload(scene)
+    got = device.render(desc)
+    want, rays = kyo.render(scene, desc)
+    _assert_same(got, want, f"light tie scene {order}")
+    assert device.stats().rays == rays
+
+
 def test_debug_sampler(device):
     scene = cases.make_scene("cornell")
     desc = ky.render_desc(cases.W, cases.H, 2, sampler=ky.SAMPLER_DEBUG)
