@@ -246,6 +246,14 @@ int kyd_film_encode(kyd_ctx* ctx, const float* film_rgb, int width, int height, 
 int kyd_film_encode_device(kyd_ctx* ctx, const float* film_rgb_device, int width, int height, int format,
                            uint8_t* out_body_device, void* cuda_stream);
 
+/* ---- FP64 validation mode for BASELINE config 1 ---------------------------------------
+   The reference's double-precision smallpt, smallpt2pbrt/smallpt_kernel.cpp (Device::Render :403-438, Radiance :184-296:
+   recursive, no light sampling, the nine-sphere scene compiled into that file, one 32-bit LCG per sample seeded with
+   y * width + x * spp + s) on the device.  film_rgb: width * height * 3 doubles, clamp01'ed, in the reference's own
+   layout (rows bottom-up).  Independent of kyd_upload_scene.  Agrees with the reference to ~1e-12 per pixel except where
+   a last-bit difference between CUDA's and glibc's double sin/cos flips a branch (none in the test cases). */
+int kyd_render_smallpt_f64(kyd_ctx* ctx, int width, int height, int samples_per_pixel, double* film_rgb);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,7 +93,7 @@ class EntryParams(C.Structure):
 
 KYD_SYMBOLS = ["kyd_create", "kyd_destroy", "kyd_last_error", "kyd_upload_scene", "kyd_render",
                "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest",
-               "kyd_film_body_bytes", "kyd_film_header", "kyd_film_encode", "kyd_film_encode_device"]
+               "kyd_film_body_bytes", "kyd_film_header", "kyd_film_encode", "kyd_film_encode_device", "kyd_render_smallpt_f64"]
 
 # kyd_film_format
 FILM_GAMMA8, FILM_BMP24, FILM_RGBE = 0, 1, 2
@@ -130,6 +130,7 @@ def kyd():
         l.kyd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         l.kyd_set_wave_paths.argtypes = [C.c_void_p, C.c_int64]
         l.kyd_selftest.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+        l.kyd_render_smallpt_f64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.kyd_film_body_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         l.kyd_film_body_bytes.restype = C.c_int64
         l.kyd_film_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -281,6 +282,12 @@ class Device:
 
     def film_encode_device(self, film_ptr, width, height, fmt, out_ptr, stream=None):
         self._check(kyd().kyd_film_encode_device(self._ctx, C.c_void_p(film_ptr), width, height, fmt, C.c_void_p(out_ptr), C.c_void_p(stream or 0)))
+
+    def render_smallpt_f64(self, width, height, samples_per_pixel):
+        """FP64 validation mode: the reference's double-precision smallpt.  Returns film[h, w, 3] float64, rows bottom-up."""
+        out = np.empty((height, width, 3), np.float64)
+        self._check(kyd().kyd_render_smallpt_f64(self._ctx, width, height, samples_per_pixel, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def set_wave_paths(self, paths):
         self._check(kyd().kyd_set_wave_paths(self._ctx, paths))

@@ -524,6 +524,31 @@ int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64
     return KYD_OK;
 }
 
+int kyd_render_smallpt_f64(kyd_ctx* ctx, int width, int height, int samples_per_pixel, double* film_rgb)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    if (width <= 0 || height <= 0 || height > 65535 || samples_per_pixel <= 0) return fail(ctx, KYD_ERR_INVALID, "bad film size / sample count");
+    if (!film_rgb) return fail(ctx, KYD_ERR_INVALID, "film pointer is null");
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = sizeof(double) * 3 * (size_t)width * height;
+    double* dev = nullptr;
+    KYD_CUDA(ctx, cudaMalloc(&dev, bytes));
+    cudaError_t e = cudaEventRecord(ctx->ev_begin, ctx->stream);
+    if (e == cudaSuccess) e = launch_smallpt_f64(width, height, samples_per_pixel, dev, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_end, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(film_rgb, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev);
+    KYD_CUDA(ctx, e);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
+    ctx->stats = kyd_stats{};
+    ctx->stats.samples = (uint64_t)width * height * samples_per_pixel;
+    ctx->stats.kernel_launches = 1;
+    ctx->stats.device_ms = ms;
+    return KYD_OK;
+}
+
 int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths)
 {
     if (!ctx) return KYD_ERR_INVALID;

@@ -64,6 +64,9 @@ void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, u
 // out_dev 4-byte aligned
 cudaError_t launch_film_encode(int device, int sm_count, const float* film_dev, int width, int height, int format, uint8_t* out_dev, cudaStream_t stream);
 
+// FP64 smallpt validation mode (kyd_smallpt.cu)
+cudaError_t launch_smallpt_f64(int width, int height, int samples_per_pixel, double* film_dev, cudaStream_t stream);
+
 void free_wave_buffers(WaveBuffers& w);
 // (re)allocates the wavefront buffers for `capacity` path slots and `lights` lights; returns a cudaError_t
 int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights);

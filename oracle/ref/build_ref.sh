@@ -56,4 +56,13 @@ gcc -O2 -fPIC -fno-builtin -fvisibility=hidden -c "$here/crlibm_shim.c" -o "$out
 g++ $CXXFLAGS -DKY_ORACLE_DETERMINISTIC -shared "$here/ref_addon.cpp" "$out/crlibm_shim.o" \
     -Wl,-Bsymbolic -o "$out/libky_ref_det.so"
 
+# ---- the FP64 smallpt of the teaching ladder: smallpt2pbrt/smallpt_kernel.cpp, CPU_RENDER ----
+#   S1  smallpt_kernel.cpp:440-  main() (MSVC-only fopen_s / errno_t, writes a ppm)  -> cut off
+#   S2  smallpt_kernel.cpp:417   per-row progress fprintf                            -> removed (I/O only)
+src="$out/smallpt_kernel_ref.cpp"
+cp "$ref/smallpt2pbrt/smallpt_kernel.cpp" "$src"
+patch1 S1 '/^int main(int argc, char\* argv\[\])/,$d' '^int main(int argc, char\* argv\[\])'
+patch1 S2 '/fprintf(stderr, "\\rRendering (%d spp) %5.2f%%"/d' 'fprintf(stderr, "\\rRendering (%d spp) %5.2f%%"'
+g++ -std=c++20 -O2 -ffp-contract=off -fopenmp -fPIC -w -I"$out" -shared "$here/smallpt_addon.cpp" -o "$out/libsmallpt_kernel_ref.so"
+
 echo "build_ref: built $(ls "$out"/*.so | tr '\n' ' ')"

@@ -156,3 +156,7 @@ def light_tie_scene(order):
     copy.shape, copy.material, copy.area_light = surfaces[lit].shape, len(materials), -1
     surfaces = [copy] + surfaces if order == "first" else surfaces + [copy]
     return CustomScene(base, shapes, materials + [m], lights, surfaces, base.desc.environment_light)
+
+
+# ---- FP64 smallpt validation mode: (width, height, samples per pixel) ----------------------------------------------
+SMALLPT_F64_CASES = [(96, 72, 16), (64, 48, 40), (33, 17, 5)]

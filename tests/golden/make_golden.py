@@ -43,6 +43,11 @@ def film_stage():
     return out
 
 
+def smallpt_f64():
+    """Films of the reference's FP64 smallpt (smallpt2pbrt/smallpt_kernel.cpp compiled by oracle/ref/build_ref.sh)."""
+    return {f"{w}x{h}@{spp}": kyref.smallpt_f64(w, h, spp) for w, h, spp in cases.SMALLPT_F64_CASES}
+
+
 def rng(seed):
     return np.random.default_rng(seed)
 
@@ -138,4 +143,5 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, "golden_films.npz"), **films())
         np.savez_compressed(os.path.join(HERE, "golden_kat.npz"), **kats())
     np.savez_compressed(os.path.join(HERE, "golden_film_stage.npz"), **film_stage())
+    np.savez_compressed(os.path.join(HERE, "golden_smallpt_f64.npz"), **smallpt_f64())
     print("wrote", os.listdir(HERE))

@@ -106,3 +106,11 @@ def gamma_encoding(x):
     out = np.zeros(x.size, np.uint8)
     lib().kyo_gamma_encoding(C.c_int64(x.size), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return out.reshape(x.shape)
+
+
+def smallpt_f64(width, height, samples_per_pixel):
+    """C restatement of the reference's FP64 smallpt (oracle/smallpt_f64.c): film[h, w, 3] float64, rows bottom-up."""
+    out = np.zeros((height, width, 3), np.float64)
+    rc = lib().kyo_smallpt_f64(C.c_int(width), C.c_int(height), C.c_int(samples_per_pixel), out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out

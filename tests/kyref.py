@@ -157,3 +157,20 @@ def gamma_encoding(x, kind="verbatim"):
     out = np.zeros(x.size, np.uint8)
     lib(kind).kyref_gamma_encoding(C.c_longlong(x.size), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
     return out.reshape(x.shape)
+
+
+_smallpt = None
+
+
+def smallpt_available():
+    return os.path.exists(os.path.join(REF_DIR, "libsmallpt_kernel_ref.so"))
+
+
+def smallpt_f64(width, height, samples_per_pixel):
+    """The reference's own smallpt_kernel.cpp (CPU_RENDER), compiled by oracle/ref/build_ref.sh."""
+    global _smallpt
+    if _smallpt is None:
+        _smallpt = C.CDLL(os.path.join(REF_DIR, "libsmallpt_kernel_ref.so"))
+    out = np.zeros((height, width, 3), np.float64)
+    assert _smallpt.smallpt_ref_render(C.c_int(width), C.c_int(height), C.c_int(samples_per_pixel), out.ctypes.data_as(C.c_void_p)) == 0
+    return out
