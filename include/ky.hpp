@@ -254,9 +254,35 @@ public:
     int device_sampler() const override { return KYD_SAMPLER_LCG48; }
     uint64_t device_seed() const override { return seed_; }
 
-private:
+protected:
     uint64_t seed_{};
     uint64_t state_{};
+};
+
+// smallpt's tent filter on a 2x2 sub-pixel grid (smallpt2pbrt/smallpt_rewrite.cpp:397-475 TrapezoidalSampler) over the
+// counter-seeded LCG, in float.  samples_per_pixel counts every sample of the pixel and must be a multiple of 4;
+// sample s belongs to sub-pixel s / (spp / 4), sub-pixel after sub-pixel like the original.
+class trapezoidal_sampler_t : public lcg48_sampler_t
+{
+public:
+    using lcg48_sampler_t::lcg48_sampler_t;
+
+    std::unique_ptr<sampler_t> clone() override { return std::make_unique<trapezoidal_sampler_t>(samples_per_pixel_, seed_); }
+
+    camera_sample_t get_camera_sample(point2_t p_film) override
+    {
+        uint64_t key = (uint64_t)current_sample_index_ | ((uint64_t)(int)p_film.x << 24) | ((uint64_t)(int)p_film.y << 40);
+        state_ = mix64(seed_ * 0x9E3779B97F4A7C15ull + key) >> 16;
+        int sub_pixel = current_sample_index_ / (samples_per_pixel_ / 4);
+        int sub_x = sub_pixel % 2, sub_y = sub_pixel / 2;
+        float random1 = 2 * get_float();
+        float random2 = 2 * get_float();
+        float delta_x = random1 < 1 ? std::sqrt(random1) - 1 : 1 - std::sqrt(2 - random1);
+        float delta_y = random2 < 1 ? std::sqrt(random2) - 1 : 1 - std::sqrt(2 - random2);
+        return { p_film + vec2_t{ ((float)sub_x + delta_x + 0.5f) / 2, ((float)sub_y + delta_y + 0.5f) / 2 } };
+    }
+
+    int device_sampler() const override { return KYD_SAMPLER_TRAPEZOIDAL; }
 };
 
 // The reference's random_sampler_t restarts mt19937_64(1234) on every image ROW and consumes a

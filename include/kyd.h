@@ -145,7 +145,10 @@ enum kyd_lighting
 enum kyd_sampler
 {
     KYD_SAMPLER_LCG48 = 0,  /* counter-seeded 48-bit LCG, the contract of DESIGN.md "Sampling" */
-    KYD_SAMPLER_DEBUG = 1   /* debug_sampler_t: every draw is 0.5, ky.cpp:922-947 */
+    KYD_SAMPLER_DEBUG = 1,  /* debug_sampler_t: every draw is 0.5, ky.cpp:922-947 */
+    KYD_SAMPLER_TRAPEZOIDAL = 2 /* LCG48 with tent-filtered 2x2 sub-pixel camera samples (smallpt's filter,
+                               smallpt2pbrt/smallpt_rewrite.cpp:397-475, in float): spp counts all samples of a pixel and
+                               must be a multiple of 4; sample s belongs to sub-pixel s / (spp / 4) */
 };
 
 enum kyd_render_flags

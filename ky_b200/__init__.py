@@ -25,7 +25,7 @@ INT_SIMPLE_PT_RECURSION, INT_PT_RECURSION, INT_PT_RECURSION_DEFERED, INT_PT_ITER
 
 DS_IDLE, DS_BSDF, DS_LIGHT, DS_BSDF_MIS, DS_LIGHT_MIS, DS_BOTH_MIS = 0, 4, 8, 16, 32, 48
 LIGHTING_EMIT, LIGHTING_DIRECT, LIGHTING_INDIRECT, LIGHTING_ALL = 1, 2, 4, 31
-SAMPLER_LCG48, SAMPLER_DEBUG = 0, 1
+SAMPLER_LCG48, SAMPLER_DEBUG, SAMPLER_TRAPEZOIDAL = 0, 1, 2
 FLAG_CLAMP, FLAG_FUSED, FLAG_ACCUMULATE, FLAG_SPLIT_LIGHT_SAMPLE = 1, 2, 4, 8
 
 # scenes of ky_host_scene_create

@@ -124,8 +124,10 @@ int validate(kyd_ctx* ctx, const kyd_render_desc* d)
     default:
         return fail(ctx, KYD_ERR_INVALID, "unsupported direct_sample_enum_t value");
     }
-    if (d->sampler != KYD_SAMPLER_LCG48 && d->sampler != KYD_SAMPLER_DEBUG)
+    if (d->sampler != KYD_SAMPLER_LCG48 && d->sampler != KYD_SAMPLER_DEBUG && d->sampler != KYD_SAMPLER_TRAPEZOIDAL)
         return fail(ctx, KYD_ERR_INVALID, "unsupported sampler");
+    if (d->sampler == KYD_SAMPLER_TRAPEZOIDAL && (d->spp < 4 || d->spp % 4 != 0))
+        return fail(ctx, KYD_ERR_INVALID, "the trapezoidal sampler needs spp to be a multiple of 4 (2x2 sub-pixels)");
     if (d->max_depth < 0) return fail(ctx, KYD_ERR_INVALID, "max_depth must be >= 0");
     return KYD_OK;
 }

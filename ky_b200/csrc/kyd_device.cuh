@@ -270,6 +270,20 @@ struct Sampler
         for (int i = 0; i < n; ++i)
             state = (state * KYD_LCG_A + KYD_LCG_C) & KYD_LCG_MASK;
     }
+    // get_camera_sample's offset inside the pixel (ky.cpp:966-974): two draws, or -- KYD_SAMPLER_TRAPEZOIDAL -- smallpt's
+    // tent filter on a 2x2 sub-pixel grid (smallpt2pbrt/smallpt_rewrite.cpp:449-466 in float; sub-pixel = sample / (spp / 4))
+    KYD_DEV float2 camera_jitter(int kind, int spp, int sample_index)
+    {
+        if (kind != KYD_SAMPLER_TRAPEZOIDAL)
+            return get_float2();
+        const int sub_pixel = sample_index / (spp / 4);
+        const int sub_x = sub_pixel % 2, sub_y = sub_pixel / 2;
+        const float random1 = 2 * get_float();
+        const float random2 = 2 * get_float();
+        const float delta_x = random1 < 1 ? __fsqrt_rn(random1) - 1 : 1 - __fsqrt_rn(2 - random1);
+        const float delta_y = random2 < 1 ? __fsqrt_rn(random2) - 1 : 1 - __fsqrt_rn(2 - random2);
+        return make_float2(((float)sub_x + delta_x + 0.5f) / 2, ((float)sub_y + delta_y + 0.5f) / 2);
+    }
 };
 
 // patch P5 of oracle/ref/build_ref.sh: stateless plastic lobe draw

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128) k_render_pixels(RenderParams rp, float* _
         {
             Sampler smp;
             smp.start(rp.sampler, rp.seed, x, y, s);
-            float2 jitter = smp.get_float2(); // get_camera_sample ky.cpp:3714, 971-974
+            float2 jitter = smp.camera_jitter(rp.sampler, rp.spp, s); // get_camera_sample ky.cpp:3714, 971-974
             Ray r = generate_ray((float)x + jitter.x, (float)y + jitter.y);
             float3 Li;
             if (IC == IC_PATH)
@@ -571,7 +571,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
         }
         traits = (all_rect && scene.n_lights == 1) ? TRAITS_AREA_RECTANGLE : all_sphere ? TRAITS_AREA_SPHERE : TRAITS_ANY;
     }
-    const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler == KYD_SAMPLER_LCG48 &&
+    const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG &&
                      !(rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE);
     // the headline kernels trace a single light's queries inside shade: no light-sampling lines, no shadow stage
     if (hot && scene.n_lights == 1)

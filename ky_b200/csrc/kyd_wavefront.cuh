@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, De
         const int x = pixel % wp.rp.width, y = pixel / wp.rp.width;
         Sampler smp;
         smp.start(wp.rp.sampler, wp.rp.seed, x, y, s);
-        float2 jitter = smp.get_float2();
+        float2 jitter = smp.camera_jitter(wp.rp.sampler, wp.rp.spp, s);
         Ray r = generate_ray((float)x + jitter.x, (float)y + jitter.y);
         float4* p = path_line(w, slot);
         store_path_ray(p, r.o, r.tmax, r.d, 0);

@@ -64,10 +64,42 @@ public:
         return { p_film + get_float2() };
     }
 
-private:
+protected:
     uint64_t seed_{};
     int sample_offset_{};
     uint64_t state_{};
+};
+
+// Tent-filtered 2x2 sub-pixel camera samples (smallpt's filter; smallpt2pbrt/smallpt_rewrite.cpp:397-475
+// TrapezoidalSampler) on top of the counter-seeded LCG, in ky's float_t: samples_per_pixel counts ALL samples of a pixel
+// (a multiple of 4); sample s belongs to sub-pixel s / (spp / 4) -- sub-pixel after sub-pixel like the original -- and
+// lands at p_film + ((sub_x + dx + 0.5) / 2, (sub_y + dy + 0.5) / 2) with dx, dy tent-distributed in [-1, 1).
+class lcg48_trapezoidal_sampler_t : public lcg48_sampler_t
+{
+public:
+    using lcg48_sampler_t::lcg48_sampler_t;
+
+    std::unique_ptr<sampler_t> clone() override
+    {
+        return std::make_unique<lcg48_trapezoidal_sampler_t>(samples_per_pixel_, seed_, sample_offset_);
+    }
+
+    camera_sample_t get_camera_sample(point2_t p_film) override
+    {
+        uint64_t x = (uint64_t)(int)p_film.x, y = (uint64_t)(int)p_film.y;
+        int sample = current_sample_index_ + sample_offset_;
+        uint64_t key = (uint64_t)sample | (x << 24) | (y << 40);
+        state_ = kyref_mix64(seed_ * 0x9E3779B97F4A7C15ull + key) >> 16;
+
+        int sub_pixel = sample / (samples_per_pixel_ / 4);
+        int sub_x = sub_pixel % 2, sub_y = sub_pixel / 2;
+        float_t random1 = 2 * get_float();
+        float_t random2 = 2 * get_float();
+        float_t delta_x = random1 < 1 ? std::sqrt(random1) - 1 : 1 - std::sqrt(2 - random1);
+        float_t delta_y = random2 < 1 ? std::sqrt(random2) - 1 : 1 - std::sqrt(2 - random2);
+        vec2_t sample_point{ ((float_t)sub_x + delta_x + 0.5f) / 2, ((float_t)sub_y + delta_y + 0.5f) / 2 };
+        return { p_film + sample_point };
+    }
 };
 
 // camera with smallpt's ray-origin push (smallpt2pbrt/smallpt_rewrite.cpp:676), needed for
@@ -271,6 +303,7 @@ int kyref_render(const kyref_render_desc* d, float* film_rgb, double* seconds, u
         std::unique_ptr<sampler_t> sampler;
         if (d->sampler == 0) sampler = std::make_unique<random_sampler_t>(d->spp);
         else if (d->sampler == 1) sampler = std::make_unique<lcg48_sampler_t>(d->spp, d->seed, d->sample_offset);
+        else if (d->sampler == 3) sampler = std::make_unique<lcg48_trapezoidal_sampler_t>(d->spp, d->seed, d->sample_offset);
         else sampler = std::make_unique<debug_sampler_t>(d->spp);
 
         auto integrator = make_integrator(d->integrator, d->max_depth, d->direct_sample);

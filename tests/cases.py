@@ -160,3 +160,14 @@ def light_tie_scene(order):
 
 # ---- FP64 smallpt validation mode: (width, height, samples per pixel) ----------------------------------------------
 SMALLPT_F64_CASES = [(96, 72, 16), (64, 48, 40), (33, 17, 5)]
+
+
+# ---- trapezoidal (tent-filter, 2x2 sub-pixel) sampler: (name, scene key, integrator, direct sample, depth, spp) -------
+def trapezoidal_cases():
+    import ky_b200 as ky
+    return [("trap/cornell/pt", "cornell", ky.INT_PT_ITERATION, ky.DS_BOTH_MIS, 5, 8),
+            ("trap/veach/pt", "veach", ky.INT_PT_ITERATION, ky.DS_BOTH_MIS, 3, 4),
+            ("trap/smallpt/pt", "smallpt", ky.INT_PT_ITERATION, ky.DS_BOTH_MIS, 5, 4),
+            ("trap/cornell/direct", "cornell", ky.INT_DIRECT_LIGHTING, ky.DS_LIGHT_MIS, 0, 4),
+            ("trap/shapes/normal", "shapes", ky.INT_NORMAL, ky.DS_BOTH_MIS, 0, 4),
+            ("trap/cornell/recursion", "cornell", ky.INT_PT_RECURSION, ky.DS_BOTH_MIS, 3, 4)]

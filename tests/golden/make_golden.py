@@ -43,6 +43,18 @@ def film_stage():
     return out
 
 
+def trapezoidal():
+    """Films of the reference driven by the trapezoidal sampler plug-in (oracle/ref/ref_addon.cpp)."""
+    out = {}
+    for name, sk, integ, ds, depth, spp in cases.trapezoidal_cases():
+        sid, flags = cases.SCENES[sk]
+        film, _, rays = kyref.render(REF_SCENE[sid], cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds,
+                                     scene_flags=flags, sampler=kyref.TRAPEZOIDAL_SAMPLER, seed=1234)
+        out[name] = film
+        out[name + "#rays"] = np.array([rays], np.uint64)
+    return out
+
+
 def smallpt_f64():
     """Films of the reference's FP64 smallpt (smallpt2pbrt/smallpt_kernel.cpp compiled by oracle/ref/build_ref.sh)."""
     return {f"{w}x{h}@{spp}": kyref.smallpt_f64(w, h, spp) for w, h, spp in cases.SMALLPT_F64_CASES}
@@ -144,4 +156,5 @@ if __name__ == "__main__":
         np.savez_compressed(os.path.join(HERE, "golden_kat.npz"), **kats())
     np.savez_compressed(os.path.join(HERE, "golden_film_stage.npz"), **film_stage())
     np.savez_compressed(os.path.join(HERE, "golden_smallpt_f64.npz"), **smallpt_f64())
+    np.savez_compressed(os.path.join(HERE, "golden_trapezoidal.npz"), **trapezoidal())
     print("wrote", os.listdir(HERE))

@@ -24,7 +24,7 @@ DEFAULT_SCENE = BOTH_SMALL | LIGHT_AREA
 # scenes of ref_addon.cpp
 CORNELL, VEACH, SMALLPT, SHAPES = 0, 1, 2, 3
 # samplers of ref_addon.cpp
-RANDOM_SAMPLER, LCG48_SAMPLER, DEBUG_SAMPLER = 0, 1, 2
+RANDOM_SAMPLER, LCG48_SAMPLER, DEBUG_SAMPLER, TRAPEZOIDAL_SAMPLER = 0, 1, 2, 3
 
 
 class RenderDesc(C.Structure):

@@ -125,6 +125,37 @@ def test_light_surface_tied_with_another_surface(device, order, ds, flags):
     assert device.stats().rays == rays
 
 
+TRAP = np.load(os.path.join(HERE, "golden", "golden_trapezoidal.npz"))
+
+
+@pytest.mark.parametrize("flags", [0, ky.FLAG_FUSED], ids=["wavefront", "pixel"])
+@pytest.mark.parametrize("case", cases.trapezoidal_cases(), ids=lambda c: c[0])
+def test_trapezoidal_sampler(device, case, flags):
+    """Tent-filtered 2x2 sub-pixel camera samples (KYD_SAMPLER_TRAPEZOIDAL) against the oracle and the reference golden,
+    one-shot and as two sample ranges accumulated on the device."""
+    import torch
+    name, sk, integ, ds, depth, spp = case
+    if flags == 0 and integ not in (ky.INT_PT_ITERATION, ky.INT_DIRECT_LIGHTING):
+        pytest.skip("only one kernel organisation exists for this integrator")
+    scene = cases.make_scene(sk)
+    device.upload(scene)
+    desc = ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds, sampler=ky.SAMPLER_TRAPEZOIDAL,
+                          flags=flags | ky.FLAG_CLAMP)
+    got = device.render(desc)
+    want, rays = kyo.render(scene, desc)
+    _assert_same(got, want, name)
+    _assert_same(got, TRAP[name], name + " (golden)")
+    assert device.stats().rays == rays == int(TRAP[name + "#rays"][0])
+    film = torch.zeros((cases.H, cases.W, 3), dtype=torch.float32, device="cuda")
+    for b, e in ((0, spp // 2 + 1), (spp // 2 + 1, spp)):
+        part = ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds, sampler=ky.SAMPLER_TRAPEZOIDAL,
+                              sample_begin=b, sample_end=e, flags=flags | ky.FLAG_ACCUMULATE)
+        device.render_device(part, film.data_ptr())
+    device.clamp_device(film.data_ptr(), film.numel())
+    torch.cuda.synchronize()
+    _assert_same(film.cpu().numpy(), want, name + " (ranges)")
+
+
 def test_debug_sampler(device):
     scene = cases.make_scene("cornell")
     desc = ky.render_desc(cases.W, cases.H, 2, sampler=ky.SAMPLER_DEBUG)

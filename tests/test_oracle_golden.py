@@ -37,6 +37,19 @@ def test_oracle_film_matches_reference_golden(case):
     assert rays == int(FILMS[name + "#rays"][0])
 
 
+TRAP = np.load(os.path.join(HERE, "golden", "golden_trapezoidal.npz"))
+
+
+@pytest.mark.parametrize("case", cases.trapezoidal_cases(), ids=lambda c: c[0])
+def test_oracle_trapezoidal_sampler_matches_reference_golden(case):
+    name, sk, integ, ds, depth, spp = case
+    scene = cases.make_scene(sk)
+    desc = ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds, sampler=ky.SAMPLER_TRAPEZOIDAL)
+    film, rays = kyo.render(scene, desc)
+    assert same_bits(film, TRAP[name]), f"{name}: {nan_safe_mismatch(film, TRAP[name])} floats differ"
+    assert rays == int(TRAP[name + "#rays"][0])
+
+
 def test_reference_mt19937_anchor():
     # rng_t(1234) first draws, from the verbatim reference build
     got = KAT["sampler/mt19937_seed1234"].view(np.uint32)[:4]

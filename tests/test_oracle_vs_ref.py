@@ -30,6 +30,21 @@ def test_oracle_equals_reference(sk, seed, offset):
     assert rays == ref_rays
 
 
+@pytest.mark.parametrize("sk", ["cornell", "veach", "shapes"])
+def test_oracle_equals_reference_with_the_trapezoidal_sampler(sk):
+    w, h, spp = 70, 40, 8
+    sid, flags = cases.SCENES[sk]
+    scene = ky.Scene(sid, w, h, flags)
+    desc = ky.render_desc(w, h, spp, seed=99, sampler=ky.SAMPLER_TRAPEZOIDAL)
+    got, rays = kyo.render(scene, desc)
+    want, _, ref_rays = kyref.render(REF_SCENE[sid], w, h, spp, scene_flags=flags, seed=99, sampler=kyref.TRAPEZOIDAL_SAMPLER)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert rays == ref_rays
+    # and it is a different image from the box-filtered one
+    plain, _ = kyo.render(scene, ky.render_desc(w, h, spp, seed=99))
+    assert not np.array_equal(plain.view(np.uint32), got.view(np.uint32))
+
+
 def test_crlibm_shim_is_linked_into_the_deterministic_build():
     # with glibc's own sinf/cosf a few percent of Lambert samples differ in the last bit
     from golden.make_golden import MATERIAL_PARAMS
