@@ -4,6 +4,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kyd_internal.h"
@@ -63,6 +64,51 @@ int fail(kyd_ctx* ctx, int code, const std::string& msg)
     } while (0)
 
 float3 f3(const float* p) { return make_float3(p[0], p[1], p[2]); }
+
+// The film comes back in chunks: chunk k is copied out of the pinned bounce buffer into the caller's (pageable) memory
+// while chunks k+1.. are still crossing PCIe, and large chunks are split over a few host threads (a single-threaded
+// memcpy of a 4K float film costs more than its PCIe transfer).
+void copy_out(void* dst, const void* src, size_t bytes)
+{
+    const size_t min_per_thread = 4u << 20;
+    size_t threads = bytes / min_per_thread;
+    if (threads > 4) threads = 4;
+    if (threads < 2) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    const size_t part = (bytes / threads + 63) & ~(size_t)63;
+    for (size_t t = 1; t < threads; ++t)
+    {
+        const size_t begin = t * part, end = (t + 1 == threads) ? bytes : (t + 1) * part;
+        pool.emplace_back([=] { memcpy((char*)dst + begin, (const char*)src + begin, end - begin); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto& th : pool) th.join();
+}
+
+int download_film(kyd_ctx* ctx, const float* dev, float* pinned, float* host, size_t bytes)
+{
+    const int chunks = bytes >= (32u << 20) ? 4 : 1;
+    const size_t part = (bytes / chunks + 255) & ~(size_t)255;
+    cudaEvent_t done[4] = {};
+    for (int k = 0; k < chunks; ++k)
+    {
+        const size_t begin = (size_t)k * part, end = (k + 1 == chunks) ? bytes : (size_t)(k + 1) * part;
+        KYD_CUDA(ctx, cudaMemcpyAsync((char*)pinned + begin, (const char*)dev + begin, end - begin, cudaMemcpyDeviceToHost, ctx->stream));
+        KYD_CUDA(ctx, cudaEventCreateWithFlags(&done[k], cudaEventDisableTiming));
+        KYD_CUDA(ctx, cudaEventRecord(done[k], ctx->stream));
+    }
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < chunks; ++k)
+    {
+        const size_t begin = (size_t)k * part, end = (k + 1 == chunks) ? bytes : (size_t)(k + 1) * part;
+        if (e == cudaSuccess) e = cudaEventSynchronize(done[k]);
+        if (e == cudaSuccess) copy_out((char*)host + begin, (const char*)pinned + begin, end - begin);
+        cudaEventDestroy(done[k]);
+    }
+    KYD_CUDA(ctx, e);
+    KYD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KYD_OK;
+}
 
 DevShape convert_shape(const kyd_shape& s)
 {
@@ -383,9 +429,7 @@ int kyd_render(kyd_ctx* ctx, const kyd_render_desc* d, float* film_rgb)
     if ((rc = ensure_pinned(ctx, floats)) != KYD_OK) return rc;
 
     if ((rc = render_to_device(ctx, d, ctx->film_dev, ctx->stream, true)) != KYD_OK) return rc;
-    KYD_CUDA(ctx, cudaMemcpyAsync(ctx->film_pinned, ctx->film_dev, floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    KYD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(film_rgb, ctx->film_pinned, floats * sizeof(float));
+    if ((rc = download_film(ctx, ctx->film_dev, ctx->film_pinned, film_rgb, floats * sizeof(float))) != KYD_OK) return rc;
     finish_stats(ctx, true);
     return KYD_OK;
 }
