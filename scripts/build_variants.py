@@ -5,6 +5,8 @@ import __graft_entry__ as g
 variants = {
     "base": [],
     "cur": [],
+    "mb5": ["-DKYD_SHADE_MIN_BLOCKS=5"],
+    "mb6": ["-DKYD_SHADE_MIN_BLOCKS=6"],
     "slowsincos": ["-DKYD_FAST_SINCOS=0"],
     "inshadow": ["-DKYD_INLINE_SHADOW=1"],
     "inshadow_mb3": ["-DKYD_INLINE_SHADOW=1", "-DKYD_SHADE_MIN_BLOCKS=3"],
