@@ -115,7 +115,7 @@ def run_reference(args):
     for i in range(args.warmup + args.steps):
         r = cpu_reference(bounded_seconds=max(2.0, 40.0 / max(1, args.warmup + args.steps)))
         if r is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libky_ref_verbatim.so was not built (needs /root/reference at build time)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/libky_ref_verbatim.so was not built (needs /root/reference at build time)"})
             return
         if i >= args.warmup:
             t.append(r)
@@ -131,10 +131,28 @@ def run_reference(args):
             "mrays_per_s": sum(r["mrays_per_s"] for r in t) / len(t),
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["cpu_baseline"]["value"] = value
-    print(json.dumps(line))
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is set), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the real stdout."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
@@ -320,7 +338,7 @@ def main():
             cb = cpu_reference()
             if cb:
                 line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mrays_per_s")}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
