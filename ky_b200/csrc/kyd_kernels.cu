@@ -607,10 +607,8 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.direct_only = direct_only ? 1 : 0;
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
 
-            T(StageTimer::RAYGEN);
-            k_raygen<<<grid256, 256, 0, stream>>>(wp, w, counters);
-            T(-1);
-            ++*launches;
+            // queue tails start at zero; the camera rays are generated inside the first intersect launch
+            cudaMemsetAsync(counters->queue, 0, sizeof(counters->queue), stream);
             for (int bounce = 0; bounce <= last_bounce; ++bounce)
             {
                 T(StageTimer::INTERSECT);

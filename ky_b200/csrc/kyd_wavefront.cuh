@@ -1,5 +1,5 @@
 // kyd_wavefront.cuh -- the wavefront organisation of path_tracing_iteration_t / direct_lighting_t
-// (reference ky.cpp:4523-4618, 4125-4155): raygen, intersect, shade (BSDF sample), light-sample (NEE + MIS
+// (reference ky.cpp:4523-4618, 4125-4155): intersect (the first one generates the camera rays), shade (BSDF sample), light-sample (NEE + MIS
 // set-up), shadow (NEE ray queries) and accumulate kernels over path state in HBM, with warp-ballot
 // compacted queues of path slots between them.  Included by kyd_kernels.cu only.
 //
@@ -201,27 +201,6 @@ KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, int 
     return Lo;
 }
 
-// ---- raygen: camera_t::generate_ray for every slot of the wave (ky.cpp:3714-3715) ----------------------
-__global__ void __launch_bounds__(256) k_raygen(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
-{
-    const int stride = gridDim.x * blockDim.x;
-    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wp.nslots; slot += stride)
-    {
-        const int pixel = wp.pixel_begin + slot % wp.npix;
-        const int s = wp.sample_begin + slot / wp.npix;
-        const int x = pixel % wp.rp.width, y = pixel / wp.rp.width;
-        Sampler smp;
-        smp.start(wp.rp.sampler, wp.rp.seed, x, y, s);
-        float2 jitter = smp.camera_jitter(wp.rp.sampler, wp.rp.spp, s);
-        Ray r = generate_ray((float)x + jitter.x, (float)y + jitter.y);
-        float4* p = path_line(w, slot);
-        store_path_ray(p, r.o, r.tmax, r.d, 0);
-        store_path_tail(p, V3(1.f, 1.f, 1.f), KYD_BLACK, smp.state);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < 16)
-        counters->queue[threadIdx.x] = threadIdx.x == Q_RAY0 ? (unsigned long long)wp.nslots : 0ull;
-}
-
 // the lobe material_t::scattering will build for this hit (ky.cpp:2587-2671); pure function of the hit
 KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 {
@@ -233,14 +212,16 @@ KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 }
 
 // ---- intersect: scene_t::intersect closest-hit query for every queued path (ky.cpp:3172-3184) -------------
-// IDENTITY: the queue is 0..n-1 (first bounce of a wave).  Hits go to the queue of their lobe; a miss ends
-// the path here (ky.cpp:4555-4563).
-template <bool IDENTITY>
+// Hits go to the queue of their lobe; a miss ends the path here (ky.cpp:4555-4563).
+// CAMERA: first bounce of a wave.  The queue is 0..nslots-1 and the rays are generated right here (camera_t::generate_ray,
+// ky.cpp:3714-3715, 1884-1892) instead of being written by a raygen kernel and read back; both sectors of the record
+// are written once, with the hit.  The host zeroes the queue tails before this launch.
+template <bool CAMERA>
 __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
     const int parity = bounce & 1;
-    const int n = (int)counters->queue[Q_RAY0 + parity];
-    if (blockIdx.x == 0 && threadIdx.x < 7)
+    const int n = CAMERA ? wp.nslots : (int)counters->queue[Q_RAY0 + parity];
+    if (!CAMERA && blockIdx.x == 0 && threadIdx.x < 7)
     {
         // tails that later kernels of this bounce push to; their previous contents were consumed by earlier kernels
         const int which[7] = { Q_RAY0 + (parity ^ 1), Q_NEE0, Q_NEE0 + 1, Q_LOBE0 + 4 * (parity ^ 1), Q_LOBE0 + 4 * (parity ^ 1) + 1,
@@ -260,10 +241,10 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
     // software pipeline of the gather: the queue entry two iterations ahead and the ray one iteration ahead are
     // loaded before the current ray is traversed, so their latency hides behind ~1000 instructions of traversal
     long long ia = base_i;
-    int slot_cur = ia < n ? (IDENTITY ? (int)ia : queue[ia]) : -1;
-    int slot_next = ia + stride < n ? (IDENTITY ? (int)(ia + stride) : queue[ia + stride]) : -1;
+    int slot_cur = ia < n ? (CAMERA ? (int)ia : queue[ia]) : -1;
+    int slot_next = ia + stride < n ? (CAMERA ? (int)(ia + stride) : queue[ia + stride]) : -1;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f), d = o;
-    if (slot_cur >= 0)
+    if (!CAMERA && slot_cur >= 0)
     {
         const float4* p0 = path_line(w, slot_cur);
         o = p0[P_ORIGIN];
@@ -275,13 +256,27 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
         int lobe = -1;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         const long long i2 = ia + 2ll * stride;
-        const int slot_next2 = i2 < n ? (IDENTITY ? (int)i2 : queue[i2]) : -1;
+        const int slot_next2 = i2 < n ? (CAMERA ? (int)i2 : queue[i2]) : -1;
         float4 o_next = make_float4(0.f, 0.f, 0.f, 0.f), d_next = o_next;
-        if (slot_next >= 0)
+        if (!CAMERA && slot_next >= 0)
         {
             const float4* pn = path_line(w, slot_next);
             o_next = pn[P_ORIGIN];
             d_next = pn[P_DIRECTION];
+        }
+        unsigned long long rng_state = 0;
+        if (CAMERA && slot_cur >= 0)
+        {
+            const int pixel = wp.pixel_begin + slot % wp.npix;
+            const int sample = wp.sample_begin + slot / wp.npix;
+            const int x = pixel % wp.rp.width, y = pixel / wp.rp.width;
+            Sampler smp;
+            smp.start(wp.rp.sampler, wp.rp.seed, x, y, sample);
+            const float2 jitter = smp.camera_jitter(wp.rp.sampler, wp.rp.spp, sample);
+            const Ray cam = generate_ray((float)x + jitter.x, (float)y + jitter.y);
+            o = make_float4(cam.o.x, cam.o.y, cam.o.z, cam.tmax);
+            d = make_float4(cam.d.x, cam.d.y, cam.d.z, __int_as_float(0));
+            rng_state = smp.state;
         }
         // the traversal runs for the whole warp, outside any divergent branch (idle lanes trace a null ray that hits
         // nothing): its loop counters and shape loads then stay in the uniform datapath
@@ -296,15 +291,23 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
             float4* p = path_line(w, slot);
             const int flags = __float_as_int(d.w);
             rays++;
+            float3 Lo_camera = KYD_BLACK;
             if (s >= 0)
             {
                 // sector 0 goes back whole, now carrying the hit
                 store_path_ray(p, r.o, t, r.d, (flags & (FLAG_PREV_SPECULAR | FLAG_PENDING_MASK)) | ((s + 1) << FLAG_SURFACE_SHIFT));
                 lobe = classify_lobe(s, r, t);
             }
-            else if (has_env && (bounce == 0 || (flags & FLAG_PREV_SPECULAR)))
+            else if (CAMERA)
             {
-                // Lo += beta * environment_lighting at the camera vertex or after a specular bounce
+                // a camera ray that leaves the scene: the sample is the environment's radiance (beta = 1) or black
+                if (has_env)
+                    Lo_camera = add(KYD_BLACK, cmulc(V3(1.f, 1.f, 1.f), environment_lighting()));
+                store_path_ray(p, r.o, o.w, r.d, 0);
+            }
+            else if (has_env && (flags & FLAG_PREV_SPECULAR))
+            {
+                // Lo += beta * environment_lighting after a specular bounce
                 PathState st;
                 unpack_path(st, o, d, p[P_BETA], p[P_TAIL]);
                 float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
@@ -312,6 +315,8 @@ __global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w,
                 store_path_ray(p, r.o, o.w, r.d, flags & FLAG_PREV_SPECULAR); // pending consumed
                 store_path_tail(p, st.beta, Lo, st.rng);
             }
+            if (CAMERA)
+                store_path_tail(p, V3(1.f, 1.f, 1.f), Lo_camera, rng_state);
         }
         push.commit(lobe_queues);                                  // the previous iteration's entries
         push.reserve(lobe >= 0 ? (1u << lobe) : 0u, slot, tails);  // this iteration's atomic, consumed next time round
