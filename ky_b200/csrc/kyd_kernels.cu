@@ -574,7 +574,8 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG &&
                      !(rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE);
     // the headline kernels trace a single light's queries inside shade: no light-sampling lines, no shadow stage
-    if (hot && scene.n_lights == 1)
+    const bool inline_queries = hot && scene.n_lights == 1;
+    if (inline_queries)
         nee = false;
 
     // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
@@ -606,6 +607,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.plane = w.capacity;
             wp.direct_only = direct_only ? 1 : 0;
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
+            wp.no_pending = (inline_queries || !nee) ? 1 : 0;
 
             // queue tails start at zero; the camera rays are generated inside the first intersect launch
             cudaMemsetAsync(counters->queue, 0, sizeof(counters->queue), stream);

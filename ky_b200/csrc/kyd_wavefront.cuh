@@ -73,6 +73,7 @@ struct WaveParams
     long long plane;          // lines between the per-light planes of the light-sampling buffer (= capacity)
     int direct_only;          // direct_lighting_t: stop after the first vertex' light loop
     int split_light_sample;   // light-sample as its own kernel (KYD_FLAG_SPLIT_LIGHT_SAMPLE) instead of inside shade
+    int no_pending;           // light queries are traced inside shade (one light, headline kernels): no path ever carries pending Ld
 };
 
 KYD_DEV float4* path_line(const WaveBuffers& w, int slot) { return w.path + (size_t)slot * PATH_UNITS; }
@@ -543,8 +544,10 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
             }
         }
     }
-    // both sectors go back whole
-    store_path_ray(p, next_o, KYD_INF, next_d, next_flags | (new_pending << FLAG_PENDING_SHIFT));
+    // both sectors go back whole; a path that ends here is read again only by k_accumulate, which needs Lo (sector 1)
+    // and -- only where light queries are deferred -- the pending count in sector 0
+    if (*out_alive || !wp.no_pending)
+        store_path_ray(p, next_o, KYD_INF, next_d, next_flags | (new_pending << FLAG_PENDING_SHIFT));
     store_path_tail(p, next_beta, Lo, rng_state);
 }
 
@@ -780,9 +783,18 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveParams wp, WaveBuffers w
         {
             const int slot = s * wp.npix + px;
             const float4* p = path_line(w, slot);
-            PathState st;
-            unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
-            float3 Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
+            float3 Li;
+            if (wp.no_pending)
+            {
+                const float4 u2 = p[P_BETA], u3 = p[P_TAIL];   // Lo lives in sector 1
+                Li = V3(u2.w, u3.x, u3.y);
+            }
+            else
+            {
+                PathState st;
+                unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
+                Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
+            }
             L = add(L, mul(Li, wp.rp.weight));
         }
         o[0] = L.x; o[1] = L.y; o[2] = L.z;
