@@ -221,7 +221,9 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         int64_t capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 24;
         if (capacity > job) capacity = job;
         if (capacity < 1024) capacity = 1024;
-        KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, ctx->scene.n_lights));
+        // light-sampling lines (128 B per light and path) and vertex records (96 B per path) only where the plan uses them
+        const WavefrontPlan plan = wavefront_plan(rp, ctx->scene);
+        KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, plan.nee ? ctx->scene.n_lights : 0, plan.split));
         ctx->timer.stream = stream;
         launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches,
                                 ctx->stage_timing ? &ctx->timer : nullptr);

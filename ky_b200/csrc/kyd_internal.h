@@ -23,7 +23,8 @@ struct DevCounters
 struct WaveBuffers
 {
     int64_t capacity = 0;
-    int max_lights = 0;
+    int max_lights = 0;           // lights the light-sampling buffer was sized for (0: not allocated)
+    bool has_vertex = false;
     // layouts: kyd_wavefront.cuh
     float4* path = nullptr;       // one 64-byte record (4 float4) per path slot
     float4* vertex = nullptr;     // 6 float4 per path slot: vertex record of the split light-sample stage
@@ -67,9 +68,29 @@ cudaError_t launch_film_encode(int device, int sm_count, const float* film_dev, 
 // FP64 smallpt validation mode (kyd_smallpt.cu)
 cudaError_t launch_smallpt_f64(int width, int height, int samples_per_pixel, double* film_dev, cudaStream_t stream);
 
+// which wavefront kernels a render uses (decides the buffers it needs, too)
+struct WavefrontPlan
+{
+    bool hot;             // headline configuration: path_tracing_iteration_t, both_mis, no debug sampler, fused light-sample
+    bool inline_queries;  // hot and one light: shade traces its own light queries (no light-sampling lines, no shadow stage)
+    bool nee;             // the shadow stage runs (light-sampling lines are written)
+    bool split;           // KYD_FLAG_SPLIT_LIGHT_SAMPLE: vertex records for the stand-alone light-sample kernel
+};
+inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scene)
+{
+    WavefrontPlan p;
+    const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
+    p.split = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) != 0;
+    p.hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG && !p.split;
+    p.inline_queries = p.hot && scene.n_lights == 1;
+    p.nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0 && !p.inline_queries;
+    return p;
+}
+
 void free_wave_buffers(WaveBuffers& w);
-// (re)allocates the wavefront buffers for `capacity` path slots and `lights` lights; returns a cudaError_t
-int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights);
+// (re)allocates the wavefront buffers for `capacity` path slots; light-sampling lines for `nee_lights` lights (0: none
+// needed) and vertex records only if `vertex`; returns a cudaError_t
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool vertex);
 
 // wavefront path: path_tracing_iteration_t and direct_lighting_t.  Adds to `launches` the kernels it launched.
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,

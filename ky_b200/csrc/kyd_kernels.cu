@@ -505,20 +505,20 @@ void free_wave_buffers(WaveBuffers& w)
     w = WaveBuffers{};
 }
 
-int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool vertex)
 {
-    if (lights < 1) lights = 1;
-    if (w.capacity >= capacity && w.max_lights >= lights)
+    if (w.capacity >= capacity && w.max_lights >= nee_lights && (w.has_vertex || !vertex))
         return cudaSuccess;
     if (capacity < w.capacity) capacity = w.capacity;
-    if (lights < w.max_lights) lights = w.max_lights;
+    if (nee_lights < w.max_lights) nee_lights = w.max_lights;
+    vertex = vertex || w.has_vertex;
     free_wave_buffers(w);
-    const size_t P = (size_t)capacity, L = (size_t)lights;
+    const size_t P = (size_t)capacity, L = (size_t)nee_lights;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     ok(alloc_array(&w.path, 4 * P));
-    ok(alloc_array(&w.vertex, 6 * P));
-    ok(alloc_array(&w.nee, 8 * L * P));
+    if (vertex) ok(alloc_array(&w.vertex, 6 * P));
+    if (L > 0) ok(alloc_array(&w.nee, 8 * L * P));
     ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P));
     for (int c = 0; c < 4; ++c) ok(alloc_array(&w.queue_lobe[c], P));
     for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_nee[c], P));
@@ -528,7 +528,8 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int lights)
         return e;
     }
     w.capacity = capacity;
-    w.max_lights = lights;
+    w.max_lights = nee_lights;
+    w.has_vertex = vertex;
     return cudaSuccess;
 }
 
@@ -556,8 +557,10 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     const long long npix_total = (long long)rp.width * rp.height;
     const int nsamples = rp.sample_end - rp.sample_begin;
     const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
-    bool nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0;
     const int last_bounce = direct_only ? 0 : rp.max_depth;
+    // the headline kernels trace a single light's queries inside shade: no light-sampling lines, no shadow stage
+    const WavefrontPlan plan = wavefront_plan(rp, scene);
+    const bool hot = plan.hot, nee = plan.nee;
 
     // scene traits and the compiled-out headline configuration select the shade instantiation (kyd_wavefront.cuh)
     int traits = TRAITS_ANY;
@@ -571,12 +574,6 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
         }
         traits = (all_rect && scene.n_lights == 1) ? TRAITS_AREA_RECTANGLE : all_sphere ? TRAITS_AREA_SPHERE : TRAITS_ANY;
     }
-    const bool hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG &&
-                     !(rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE);
-    // the headline kernels trace a single light's queries inside shade: no light-sampling lines, no shadow stage
-    const bool inline_queries = hot && scene.n_lights == 1;
-    if (inline_queries)
-        nee = false;
 
     // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
     const int grid256 = sm_count * 16, grid128 = sm_count * 24;
@@ -607,7 +604,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.plane = w.capacity;
             wp.direct_only = direct_only ? 1 : 0;
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
-            wp.no_pending = (inline_queries || !nee) ? 1 : 0;
+            wp.no_pending = nee ? 0 : 1;
 
             // queue tails start at zero; the camera rays are generated inside the first intersect launch
             cudaMemsetAsync(counters->queue, 0, sizeof(counters->queue), stream);
