@@ -219,6 +219,7 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         // launch gaps and wave tails cost more than L2 residency of the path state would win.
         const int64_t job = (int64_t)d->width * d->height * (int64_t)(d->sample_end - d->sample_begin);
         int64_t capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 24;
+        if (capacity > ((int64_t)1 << 24)) capacity = (int64_t)1 << 24;   // pair-queue entries carry the slot in 24 bits
         if (capacity > job) capacity = job;
         if (capacity < 1024) capacity = 1024;
         // light-sampling lines (128 B per light and path) and vertex records (96 B per path) only where the plan uses them

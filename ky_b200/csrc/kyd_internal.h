@@ -33,7 +33,8 @@ struct WaveBuffers
     int* queue_a = nullptr;        // ray queues (ping-pong by bounce parity)
     int* queue_b = nullptr;
     int* queue_lobe[4] = {};       // hit paths sorted by BSDF lobe: Lambert, mirror, glass, Phong (LOBE_* order)
-    int* queue_nee[2] = {};        // vertices that sample lights: Lambert, Phong
+    int* queue_nee[2] = {};        // vertices for the stand-alone light-sample stage (split mode): Lambert, Phong
+    int* queue_pair[2] = {};       // (vertex, light) pairs with a light-sampling line: slot | light << 24; capacity * lights entries
 };
 
 // optional per-stage device timing (KYD_STAGE_TIMING=1): CUDA events around every kernel of the wavefront

@@ -499,7 +499,7 @@ static cudaError_t alloc_array(T** p, size_t count)
 void free_wave_buffers(WaveBuffers& w)
 {
     void* ptrs[] = { w.path, w.vertex, w.nee, w.queue_a, w.queue_b, w.queue_lobe[0], w.queue_lobe[1],
-                     w.queue_lobe[2], w.queue_lobe[3], w.queue_nee[0], w.queue_nee[1] };
+                     w.queue_lobe[2], w.queue_lobe[3], w.queue_nee[0], w.queue_nee[1], w.queue_pair[0], w.queue_pair[1] };
     for (void* p : ptrs)
         if (p) cudaFree(p);
     w = WaveBuffers{};
@@ -522,6 +522,8 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool v
     ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P));
     for (int c = 0; c < 4; ++c) ok(alloc_array(&w.queue_lobe[c], P));
     for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_nee[c], P));
+    if (L > 0)
+        for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_pair[c], L * P));
     if (e != cudaSuccess)
     {
         free_wave_buffers(w);
@@ -533,21 +535,32 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool v
     return cudaSuccess;
 }
 
-template <int TRAITS, bool HOT>
+// the mirror and glass kernels sample no lights: one instantiation serves both light counts
+template <int TRAITS, bool HOT, int NL>
 static void launch_shade_lobes(int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
 {
-    k_shade<LOBE_LAMBERT, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
-    k_shade<LOBE_PHONG, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
-    k_shade<LOBE_MIRROR, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
-    k_shade<LOBE_FRESNEL, TRAITS, HOT><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    constexpr int NL_SPECULAR = HOT ? NL_ONE : NL_ANY;
+    k_shade<LOBE_LAMBERT, TRAITS, HOT, NL><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_PHONG, TRAITS, HOT, NL><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_MIRROR, TRAITS, HOT, NL_SPECULAR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_FRESNEL, TRAITS, HOT, NL_SPECULAR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
 }
 
-static void launch_shade(int traits, bool hot, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
+static void launch_shade(int traits, bool hot, bool one_light, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w,
+                         DevCounters* counters, int bounce)
 {
-    if (!hot) launch_shade_lobes<TRAITS_ANY, false>(grid, stream, wp, w, counters, bounce);
-    else if (traits == TRAITS_AREA_RECTANGLE) launch_shade_lobes<TRAITS_AREA_RECTANGLE, true>(grid, stream, wp, w, counters, bounce);
-    else if (traits == TRAITS_AREA_SPHERE) launch_shade_lobes<TRAITS_AREA_SPHERE, true>(grid, stream, wp, w, counters, bounce);
-    else launch_shade_lobes<TRAITS_ANY, true>(grid, stream, wp, w, counters, bounce);
+    if (!hot) launch_shade_lobes<TRAITS_ANY, false, NL_ANY>(grid, stream, wp, w, counters, bounce);
+    else if (traits == TRAITS_AREA_RECTANGLE) launch_shade_lobes<TRAITS_AREA_RECTANGLE, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
+    else if (traits == TRAITS_AREA_SPHERE)
+    {
+        if (one_light) launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
+        else launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_MANY>(grid, stream, wp, w, counters, bounce);
+    }
+    else
+    {
+        if (one_light) launch_shade_lobes<TRAITS_ANY, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
+        else launch_shade_lobes<TRAITS_ANY, true, NL_MANY>(grid, stream, wp, w, counters, bounce);
+    }
 }
 
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
@@ -617,7 +630,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                     k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
                 T(-1);
                 T(StageTimer::SHADE);
-                launch_shade(traits, hot, grid128, stream, wp, w, counters, bounce);
+                launch_shade(traits, hot, plan.inline_queries, grid128, stream, wp, w, counters, bounce);
                 T(-1);
                 *launches += 5;
                 if (nee)
@@ -630,7 +643,10 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                         ++*launches;
                     }
                     T(StageTimer::SHADOW);
-                    k_shadow<<<grid256, 256, 0, stream>>>(wp, w, counters);
+                    if (wp.split_light_sample)
+                        k_shadow<false><<<grid256, 256, 0, stream>>>(wp, w, counters);
+                    else
+                        k_shadow<true><<<grid256, 256, 0, stream>>>(wp, w, counters);
                     T(-1);
                     ++*launches;
                 }

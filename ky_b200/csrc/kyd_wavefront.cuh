@@ -46,12 +46,17 @@
 namespace kyd {
 
 // queue tails in DevCounters::queue
-enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong) */, Q_LOBE0 = 4 /* + 4 * parity + lobe */ };
+enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong): vertices, split light-sample stage only */,
+       Q_LOBE0 = 4 /* + 4 * parity + lobe */, Q_PAIR0 = 12 /* +lobe: (vertex, light) pairs with a live light query */ };
 
 #ifndef KYD_SHADE_MIN_BLOCKS
 #define KYD_SHADE_MIN_BLOCKS 4
 #endif
 #define SHADE_THREADS 128
+
+// number of lights as a compile-time property of the headline shade kernels: one light = its queries are traced inside
+// shade, several = one light-sampling line per (vertex, light) for the shadow stage; NL_ANY decides at run time
+enum { NL_ANY = 0, NL_ONE = 1, NL_MANY = 2 };
 
 // float4 units of the records
 enum { P_ORIGIN = 0, P_DIRECTION = 1, P_BETA = 2, P_TAIL = 3, PATH_UNITS = 4 };
@@ -59,7 +64,11 @@ enum { N_LIGHT_O = 0, N_LIGHT_D = 1, N_LIGHT_VALUE = 2, N_MIXED = 3, N_BSDF_O = 
 enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_BETA = 5, VERTEX_UNITS = 6 };
 
 // flags word of a path (w of the direction unit)
-enum { FLAG_PREV_SPECULAR = 1, FLAG_PENDING_SHIFT = 4, FLAG_PENDING_MASK = 0x1f << 4, FLAG_SURFACE_SHIFT = 12 };
+// bit 0: previous vertex was specular; bits 4-11: 1 + hit surface; bits 16-31: lights whose estimator value is pending
+// (a light-sampling line was written for them at the previous vertex and the shadow stage resolves it)
+enum { FLAG_PREV_SPECULAR = 1, FLAG_SURFACE_SHIFT = 4, FLAG_SURFACE_MASK = 0xff << 4, FLAG_PENDING_SHIFT = 16, FLAG_PENDING_MASK = (int)0xffff0000u };
+// entry of the pair queues: path slot | light << 24 (a wave holds at most 2^24 paths, a scene at most 16 lights)
+enum { PAIR_LIGHT_SHIFT = 24, PAIR_SLOT_MASK = (1 << 24) - 1 };
 // flags word of a light-sampling line (w of the light query's direction unit)
 // (bits 8..: 1 + the light's surface when the BSDF-sampled query is in its occlusion form, NeeRay::light_surface)
 enum { NEE_REF_BSDF = 1, NEE_REF_LIGHT = 2, NEE_BSDF_LIVE = 4, NEE_LIGHT_SURFACE_SHIFT = 8 };
@@ -150,6 +159,54 @@ struct WarpPush
     }
 };
 
+// Pushes a variable number of (vertex, light) pairs per lane -- one entry per set bit of `mask` -- with one atomic per
+// warp and iteration, deferred like WarpPush: a warp scan of the per-lane counts, lane 0 reserves the warp's range.
+struct PairPush
+{
+    unsigned mask;             // this lane's lights of the iteration whose entries are not written yet
+    int slot;
+    unsigned offset;           // entries of lower lanes
+    unsigned long long base;   // lane 0: first index reserved
+    bool pending;              // warp-uniform
+
+    KYD_DEV void init() { pending = false; mask = 0; slot = 0; offset = 0; base = 0; }
+
+    KYD_DEV void reserve(unsigned mask_, int slot_, unsigned long long* tail)
+    {
+        __syncwarp();
+        pending = __any_sync(0xffffffffu, mask_ != 0u);
+        if (!pending)
+            return;
+        mask = mask_;
+        slot = slot_;
+        const int lane = threadIdx.x & 31;
+        const unsigned count = __popc(mask_);
+        unsigned inclusive = count;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inclusive, d);
+            if (lane >= d) inclusive += v;
+        }
+        offset = inclusive - count;
+        const unsigned total = __shfl_sync(0xffffffffu, inclusive, 31);
+        base = 0;
+        if (lane == 0)
+            base = atomicAdd(tail, (unsigned long long)total);
+    }
+
+    KYD_DEV void commit(int* queue)
+    {
+        if (!pending)
+            return;
+        __syncwarp();
+        unsigned long long idx = __shfl_sync(0xffffffffu, base, 0) + offset;
+        for (unsigned m = mask; m != 0u; m &= m - 1u)
+            queue[idx++] = slot | ((__ffs(m) - 1) << PAIR_LIGHT_SHIFT);
+        pending = false;
+    }
+};
+
 // ---- path record ------------------------------------------------------------------------------------------
 struct PathState
 {
@@ -159,8 +216,8 @@ struct PathState
     float3 beta, Lo;
     unsigned long long rng;
 
-    KYD_DEV int pending() const { return (flags & FLAG_PENDING_MASK) >> FLAG_PENDING_SHIFT; }
-    KYD_DEV int surface() const { return (flags >> FLAG_SURFACE_SHIFT) - 1; }
+    KYD_DEV unsigned pending() const { return (unsigned)flags >> FLAG_PENDING_SHIFT; }
+    KYD_DEV int surface() const { return ((flags & FLAG_SURFACE_MASK) >> FLAG_SURFACE_SHIFT) - 1; }
 };
 
 KYD_DEV void unpack_path(PathState& s, float4 u0, float4 u1, float4 u2, float4 u3)
@@ -184,17 +241,19 @@ KYD_DEV void store_path_tail(float4* p, float3 beta, float3 Lo, unsigned long lo
     p[P_TAIL] = make_float4(Lo.y, Lo.z, __uint_as_float((unsigned)rng), __uint_as_float((unsigned)(rng >> 32)));
 }
 
-// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576
-KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, int pending, float3 Lo)
+// Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576.  `pending` = the lights that
+// got a light-sampling line; the others' values are exactly +0 (no query of theirs could contribute) and adding +0 to
+// the running sum, which starts at +0 and therefore is never -0, changes nothing -- so they are skipped, in light order.
+KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsigned pending, float3 Lo)
 {
-    if (pending > 0)
+    if (pending != 0)
     {
-        const float4* line0 = nee_line(w, plane, 0, slot);
+        const float4* line0 = nee_line(w, plane, __ffs(pending) - 1, slot);
         float4 e0 = line0[N_RESULT], vb = line0[N_VERTEX_BETA];
         float3 Ld = add(KYD_BLACK, V3(e0.x, e0.y, e0.z));
-        for (int l = 1; l < pending; ++l)
+        for (unsigned rest = pending & (pending - 1); rest != 0; rest &= rest - 1)
         {
-            float4 e = nee_line(w, plane, l, slot)[N_RESULT];
+            float4 e = nee_line(w, plane, __ffs(rest) - 1, slot)[N_RESULT];
             Ld = add(Ld, V3(e.x, e.y, e.z));
         }
         Lo = add(Lo, cmulc(V3(vb.x, vb.y, vb.z), Ld));
@@ -217,16 +276,19 @@ KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 // CAMERA: first bounce of a wave.  The queue is 0..nslots-1 and the rays are generated right here (camera_t::generate_ray,
 // ky.cpp:3714-3715, 1884-1892) instead of being written by a raygen kernel and read back; both sectors of the record
 // are written once, with the hit.  The host zeroes the queue tails before this launch.
+#ifndef KYD_INTERSECT_MIN_BLOCKS
+#define KYD_INTERSECT_MIN_BLOCKS 1
+#endif
 template <bool CAMERA>
-__global__ void __launch_bounds__(256) k_intersect(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
+__global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
     const int parity = bounce & 1;
     const int n = CAMERA ? wp.nslots : (int)counters->queue[Q_RAY0 + parity];
-    if (!CAMERA && blockIdx.x == 0 && threadIdx.x < 7)
+    if (!CAMERA && blockIdx.x == 0 && threadIdx.x < 9)
     {
         // tails that later kernels of this bounce push to; their previous contents were consumed by earlier kernels
-        const int which[7] = { Q_RAY0 + (parity ^ 1), Q_NEE0, Q_NEE0 + 1, Q_LOBE0 + 4 * (parity ^ 1), Q_LOBE0 + 4 * (parity ^ 1) + 1,
-                               Q_LOBE0 + 4 * (parity ^ 1) + 2, Q_LOBE0 + 4 * (parity ^ 1) + 3 };
+        const int which[9] = { Q_RAY0 + (parity ^ 1), Q_NEE0, Q_NEE0 + 1, Q_LOBE0 + 4 * (parity ^ 1), Q_LOBE0 + 4 * (parity ^ 1) + 1,
+                               Q_LOBE0 + 4 * (parity ^ 1) + 2, Q_LOBE0 + 4 * (parity ^ 1) + 3, Q_PAIR0, Q_PAIR0 + 1 };
         counters->queue[which[threadIdx.x]] = 0;
     }
     const int* __restrict__ queue = parity ? w.queue_b : w.queue_a;
@@ -411,9 +473,9 @@ KYD_DEV float3 nee_resolve_pair(int ds, const NeeRay& qb, const NeeRay& ql, Shad
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
 // HOT: the headline configuration (path_tracing_iteration_t, both_mis, LCG48 sampler, light-sample inside shade)
 // with those run-time switches compiled out; !HOT reads them from the parameters
-template <int LOBE, int TRAITS, bool HOT>
-KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, bool* out_nee,
-                          ShadeCounts* counts, float4 rec0, float4 rec1, float4 rec2, float4 rec3)
+template <int LOBE, int TRAITS, bool HOT, int NL>
+KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, unsigned* out_pairs,
+                          bool* out_split_vertex, ShadeCounts* counts, float4 rec0, float4 rec1, float4 rec2, float4 rec3)
 {
     const int ds = HOT ? (int)KYD_DS_BOTH_MIS : wp.rp.direct_sample;
     const bool direct_only = HOT ? false : wp.direct_only != 0;
@@ -431,7 +493,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
 
     // light gathered at the previous vertex (see file header)
     float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
-    int new_pending = 0;
+    unsigned new_pending = 0;   // lights that get a light-sampling line at this vertex
 
     HitGeom g = shape_hit_geom(c_scene.surf_shape[surface], r, st.t);
 
@@ -473,9 +535,10 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                     v[V_COLOR] = make_float4(b.a.x, b.a.y, b.a.z, 0.f);
                     v[V_RNG] = make_float4(__uint_as_float((unsigned)smp.state), __uint_as_float((unsigned)(smp.state >> 32)), 0.f, 0.f);
                     v[V_BETA] = make_float4(beta.x, beta.y, beta.z, 0.f);
-                    new_pending = n_lights;
+                    new_pending = (1u << n_lights) - 1u;   // the light-sample kernel writes a line for every light
+                    *out_split_vertex = true;
                 }
-                else if (TRAITS == TRAITS_AREA_RECTANGLE || n_lights == 1)
+                else if (NL == NL_ONE || (NL == NL_ANY && (TRAITS == TRAITS_AREA_RECTANGLE || n_lights == 1)))
                 {
                     // the common case keeps both queries in registers and writes nothing when neither can contribute
                     NeeRay qb, ql;
@@ -493,24 +556,45 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                         {
                             qb.ref_query = ql.ref_query = false; // counted here
                             store_nee_line(nee_line(w, wp.plane, 0, slot), qb, ql, beta);
-                            new_pending = 1;
+                            new_pending = 1u;
                         }
                     }
                 }
-                else if (TRAITS != TRAITS_AREA_RECTANGLE)
+                else if (NL != NL_ONE && TRAITS != TRAITS_AREA_RECTANGLE)
                 {
-                    // several lights: one line per (vertex, light); the shadow stage gives every query its own thread
+                    // several lights: one line per (vertex, light) with a query that can contribute; the shadow stage
+                    // gives every such pair its own thread
                     Sampler ls = smp;
                     for (int l = 0; l < n_lights; ++l)
                     {
                         NeeRay qb, ql;
                         light_sample_pair<TRAITS>(ds, g, b, l, ls, &qb, &ql);
-                        store_nee_line(nee_line(w, wp.plane, l, slot), qb, ql, beta);
+                        counts->ref_rays += (qb.ref_query ? 1u : 0u) + (ql.ref_query ? 1u : 0u);
+                        if (qb.active || ql.active)
+                        {
+                            qb.ref_query = ql.ref_query = false; // counted here
+                            store_nee_line(nee_line(w, wp.plane, l, slot), qb, ql, beta);
+                            new_pending |= 1u << l;
+                        }
                         ls.skip(4 + ((ds == KYD_DS_BSDF && !light_is_delta(c_scene.lights[l].kind)) ? 2 : 0));
                     }
-                    new_pending = n_lights;
+                    // (beta * 0 is 0 only for finite beta: a non-finite throughput keeps the reference's NaN through an
+                    // empty line of light 0, whose value the shadow stage resolves to 0)
+                    if (new_pending == 0 && !(isfinite(beta.x) && isfinite(beta.y) && isfinite(beta.z)))
+                    {
+                        NeeRay none;
+                        none.active = none.ref_query = false;
+                        none.value = KYD_BLACK;
+                        none.ray.o = none.ray.d = V3(0, 0, 0);
+                        none.ray.tmax = -1.f;
+                        none.light = 0;
+                        none.light_surface = -1;
+                        store_nee_line(nee_line(w, wp.plane, 0, slot), none, none, beta);
+                        new_pending = 1u;
+                    }
                 }
-                *out_nee = new_pending > 0;
+                if (!split_light_sample)
+                    *out_pairs = new_pending;
             }
             // sample_all_light draws 4 floats per light, plus 2 per non-delta light in `bsdf` mode
             smp.skip(4 * n_lights + (ds == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
@@ -547,11 +631,11 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     // both sectors go back whole; a path that ends here is read again only by k_accumulate, which needs Lo (sector 1)
     // and -- only where light queries are deferred -- the pending count in sector 0
     if (*out_alive || !wp.no_pending)
-        store_path_ray(p, next_o, KYD_INF, next_d, next_flags | (new_pending << FLAG_PENDING_SHIFT));
+        store_path_ray(p, next_o, KYD_INF, next_d, next_flags | (int)(new_pending << FLAG_PENDING_SHIFT));
     store_path_tail(p, next_beta, Lo, rng_state);
 }
 
-template <int LOBE, int TRAITS, bool HOT>
+template <int LOBE, int TRAITS, bool HOT, int NL>
 KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
 {
     const int parity = bounce & 1;
@@ -561,11 +645,17 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     const int stride = gridDim.x * blockDim.x;
     const int n_lights = c_scene.n_lights;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // queue 0: the next bounce's rays; queue 1: vertices whose light queries the shadow stage resolves
+    // queue 0: the next bounce's rays; queue 1: vertices for the stand-alone light-sample stage (split mode only);
+    // pair queue: (vertex, light) pairs whose light-sampling line the shadow stage resolves
     unsigned long long* const tails[2] = { &counters->queue[Q_RAY0 + (parity ^ 1)], &counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)] };
     int* const out_queues[2] = { next_queue, w.queue_nee[LOBE == LOBE_PHONG] };
+    unsigned long long* const pair_tail = &counters->queue[Q_PAIR0 + (LOBE == LOBE_PHONG)];
+    int* const pair_queue = w.queue_pair[LOBE == LOBE_PHONG];
+    constexpr bool DEFERS = !(HOT && NL == NL_ONE) && (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG);
     WarpPush<2> push;
     push.init();
+    PairPush pairs;
+    pairs.init();
     ShadeCounts counts = { 0u, 0u };
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&counters->shade_vertices, (unsigned long long)n); // traffic model of bench.py
@@ -574,7 +664,7 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     // iteration ahead
     // the single-light kernels have the registers to load the next vertex' record while this one is shaded (its queue
     // entry is then read two iterations ahead); the others would spill (profiles/r01_ab_variants.txt)
-    constexpr bool PREFETCH = HOT && TRAITS == TRAITS_AREA_RECTANGLE;
+    constexpr bool PREFETCH = HOT && NL == NL_ONE;
     long long ia = i;
     int slot_cur = ia < n ? queue[ia] : -1;
     int slot_next = ia + stride < n ? queue[ia + stride] : -1;
@@ -594,7 +684,8 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
             const float4* pn = path_line(w, slot_next);
             nx0 = pn[P_ORIGIN]; nx1 = pn[P_DIRECTION]; nx2 = pn[P_BETA]; nx3 = pn[P_TAIL];
         }
-        bool alive = false, wants_nee = false;
+        bool alive = false, split_vertex = false;
+        unsigned pair_mask = 0;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         if (slot_cur >= 0)
         {
@@ -603,10 +694,15 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
                 const float4* p0 = path_line(w, slot);
                 rec0 = p0[P_ORIGIN]; rec1 = p0[P_DIRECTION]; rec2 = p0[P_BETA]; rec3 = p0[P_TAIL];
             }
-            shade_vertex<LOBE, TRAITS, HOT>(wp, w, slot, bounce, n_lights, &alive, &wants_nee, &counts, rec0, rec1, rec2, rec3);
+            shade_vertex<LOBE, TRAITS, HOT, NL>(wp, w, slot, bounce, n_lights, &alive, &pair_mask, &split_vertex, &counts, rec0, rec1, rec2, rec3);
         }
         push.commit(out_queues);
-        push.reserve((alive ? 1u : 0u) | (wants_nee ? 2u : 0u), slot, tails);
+        push.reserve((alive ? 1u : 0u) | (split_vertex ? 2u : 0u), slot, tails);
+        if (DEFERS)
+        {
+            pairs.commit(pair_queue);
+            pairs.reserve(pair_mask, slot, pair_tail);
+        }
         if (PREFETCH)
         {
             slot_cur = slot_next;
@@ -617,15 +713,17 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
             slot_cur = slot_ahead;
     }
     push.commit(out_queues);
+    if (DEFERS)
+        pairs.commit(pair_queue);
     flush_counters(counts.ref_rays, counts.traced, counters);
 }
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
 // shades most vertices, does not pay for Phong's pow() or the dielectric's Fresnel terms)
-template <int LOBE, int TRAITS, bool HOT>
+template <int LOBE, int TRAITS, bool HOT, int NL>
 __global__ void __launch_bounds__(SHADE_THREADS, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
-    shade_queue<LOBE, TRAITS, HOT>(wp, w, counters, bounce);
+    shade_queue<LOBE, TRAITS, HOT, NL>(wp, w, counters, bounce);
 }
 
 // ---- light-sample as its own stage (KYD_FLAG_SPLIT_LIGHT_SAMPLE): one thread per (vertex, light) -------------
@@ -674,6 +772,9 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 // ---- shadow: the scene queries of the light loop and the estimators' second halves ------------------------
 // closest-hit query for the BSDF-sampled direction, occlusion query for the light-sampled point; writes
 // the estimator value of (vertex, light): Lb, Ll or 0.5 Lb + 0.5 Ll (ky.cpp:4083)
+// PAIRS: the queue holds the (vertex, light) pairs that got a line (shade wrote them); !PAIRS (split light-sample stage):
+// the queue holds vertices and every light has a line.
+template <bool PAIRS>
 __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
 {
     const int n_lights = c_scene.n_lights;
@@ -682,19 +783,32 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
     unsigned rays = 0, traced = 0;
     for (int c = 0; c < 2; ++c)
     {
-        const int n = (int)counters->queue[Q_NEE0 + c];
+        const long long n = (long long)counters->queue[(PAIRS ? Q_PAIR0 : Q_NEE0) + c];
+        const long long total = PAIRS ? n : n * n_lights;
         if (blockIdx.x == 0 && threadIdx.x == 0)
-            atomicAdd(&counters->shade_lines, (unsigned long long)n * n_lights); // lines shade wrote for this stage
-        const int* __restrict__ nee_queue = w.queue_nee[c];
-        const long long total = (long long)n * n_lights;
+            atomicAdd(&counters->shade_lines, (unsigned long long)total); // lines written for this stage
+        const int* __restrict__ nee_queue = PAIRS ? w.queue_pair[c] : w.queue_nee[c];
         // block-uniform trip count and traversals outside divergent branches (idle lanes trace null rays): the
         // traversal loops stay in the uniform datapath, as in k_intersect
         for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride)
         {
             const long long idx = base + threadIdx.x;
             const bool valid = idx < total;
-            const int l = valid ? (int)(idx / n) : 0;
-            const int slot = valid ? nee_queue[idx - (long long)l * n] : 0;
+            int l = 0, slot = 0;
+            if (valid)
+            {
+                if (PAIRS)
+                {
+                    const int entry = nee_queue[idx];
+                    l = entry >> PAIR_LIGHT_SHIFT;
+                    slot = entry & PAIR_SLOT_MASK;
+                }
+                else
+                {
+                    l = (int)(idx / n);
+                    slot = nee_queue[idx - (long long)l * n];
+                }
+            }
             float4* line = nee_line(w, wp.plane, l, slot);
             float4 lo = make_float4(0.f, 0.f, 0.f, -1.f), ld = make_float4(0.f, 0.f, 0.f, 0.f), lv = ld, mx = ld;
             if (valid)

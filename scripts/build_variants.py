@@ -5,6 +5,8 @@ import __graft_entry__ as g
 variants = {
     "base": [],
     "cur": [],
+    "imb3": ["-DKYD_INTERSECT_MIN_BLOCKS=3"],
+    "imb2": ["-DKYD_INTERSECT_MIN_BLOCKS=2"],
     "mb5": ["-DKYD_SHADE_MIN_BLOCKS=5"],
     "mb6": ["-DKYD_SHADE_MIN_BLOCKS=6"],
     "slowsincos": ["-DKYD_FAST_SINCOS=0"],
