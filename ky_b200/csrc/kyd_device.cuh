@@ -49,6 +49,11 @@ __constant__ DevScene c_scene;
 KYD_DEV float max_std(float a, float b) { return (a < b) ? b : a; }
 KYD_DEV float clamp_std(float v, float lo, float hi) { return (v < lo) ? lo : (hi < v) ? hi : v; }
 
+// A NaN radiance (the reference produces them too: 0 * inf in a throughput, about one sample in 10^8 of the Cornell box)
+// leaves the device with the bit pattern the reference's x86-64 build gives it: SSE's default NaN 0xffc00000 -- every NaN
+// on this path is born from an invalid operation and then only propagated -- where this GPU would write 0x7fffffff.
+KYD_DEV float film_value(float v) { return v != v ? __int_as_float((int)0xffc00000u) : v; }
+
 // libm contract
 KYD_MATH float cr_sin(float x) { return __double2float_rn(sin((double)x)); }
 KYD_MATH float cr_cos(float x) { return __double2float_rn(cos((double)x)); }

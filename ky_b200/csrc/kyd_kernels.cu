@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(128) k_render_pixels(RenderParams rp, float* _
         }
         if (rp.flags & KYD_FLAG_CLAMP)
             L = V3(clamp_std(L.x, 0.f, 1.f), clamp_std(L.y, 0.f, 1.f), clamp_std(L.z, 0.f, 1.f));
-        o[0] = L.x; o[1] = L.y; o[2] = L.z;
+        o[0] = film_value(L.x); o[1] = film_value(L.y); o[2] = film_value(L.z);
     }
     unsigned rays = __reduce_add_sync(0xffffffffu, cnt.rays);
     unsigned traced = __reduce_add_sync(0xffffffffu, cnt.traced);
@@ -374,7 +374,7 @@ __global__ void k_clamp(float* __restrict__ film, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-        film[i] = clamp_std(film[i], 0.f, 1.f);
+        film[i] = film_value(clamp_std(film[i], 0.f, 1.f));
 }
 
 void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream)

@@ -911,7 +911,7 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveParams wp, WaveBuffers w
             }
             L = add(L, mul(Li, wp.rp.weight));
         }
-        o[0] = L.x; o[1] = L.y; o[2] = L.z;
+        o[0] = film_value(L.x); o[1] = film_value(L.y); o[2] = film_value(L.z);
     }
 }
 

@@ -61,3 +61,21 @@ def test_baseline_config_at_full_resolution(device, cfg):
     device.clamp_device(film.data_ptr(), film.numel())
     torch.cuda.synchronize()
     assert np.array_equal(_bits(film.cpu().numpy()), _bits(one_shot))
+
+
+def test_nan_sample_keeps_the_reference_bit_pattern(device):
+    """Sample 13 of pixel (1816, 1777) of the C5 job has a NaN radiance in the reference (0 * inf in a throughput).  The film
+    must carry it with the bit pattern the reference's x86-64 build produces (SSE default NaN, 0xffc00000), in both kernel
+    organisations, clamped or not."""
+    w, h, spp = 3840, 2160, 16
+    scene = ky.Scene(ky.SCENE_CORNELL, w, h, ky.CB_DEFAULT)
+    device.upload(scene)
+    device.set_wave_paths(0)
+    for flags in (0, ky.FLAG_CLAMP, ky.FLAG_FUSED):
+        desc = ky.render_desc(w, h, spp, max_depth=5, sample_begin=13, sample_end=14, flags=flags)
+        got = device.render(desc)
+        want, rays = kyo.render(scene, desc)
+        assert np.isnan(want[1777, 1816]).all() and int(np.isnan(want).any(axis=-1).sum()) == 1
+        assert (_bits(want[1777, 1816]) == 0xFFC00000).all()
+        assert np.array_equal(_bits(got), _bits(want))
+        assert device.stats().rays == rays
