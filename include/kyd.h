@@ -41,6 +41,11 @@ enum kyd_error
 };
 
 enum { KYD_MAX_SURFACES = 64, KYD_MAX_SHAPES = 64, KYD_MAX_MATERIALS = 32, KYD_MAX_LIGHTS = 16 };
+/* Scenes with more than KYD_MAX_SURFACES surfaces (up to KYD_MAX_SURFACES_BVH, e.g. small triangle meshes) leave constant
+   memory: their surfaces live in global memory under a bounding-volume hierarchy built at upload -- the accelerator the
+   reference leaves as an empty hook (accel_t, ky.cpp:3097-3115).  Results are those of the reference's linear walk
+   (closest hit, lowest surface index among equal distances); smaller scenes keep the linear walk itself. */
+enum { KYD_MAX_SURFACES_BVH = 4000, KYD_MAX_SHAPES_BVH = 4000 };
 
 /* ---- flattened scene: one POD per reference object ------------------------------------------- */
 

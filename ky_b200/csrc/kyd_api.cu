@@ -1,6 +1,8 @@
 // kyd_api.cu -- the C ABI of include/kyd.h: context, scene upload, render orchestration.
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -29,6 +31,7 @@ struct kyd_ctx
     size_t pinned_capacity = 0;
     uint8_t* body_dev = nullptr;    // encoded image body for kyd_film_encode (host destination)
     size_t body_capacity = 0;
+    void* big_scene_dev = nullptr;  // one allocation: shapes | materials | lights | BVH nodes | BVH leaf order (large scenes)
 
     DevCounters* counters_dev = nullptr;
     DevCounters* counters_pinned = nullptr;
@@ -46,8 +49,8 @@ std::string g_create_error;
 
 // c_scene is one symbol per device: remember which context's scene it holds
 std::mutex g_scene_mutex;
-const kyd_ctx* g_scene_owner[64] = {};
-unsigned long long g_scene_owner_generation[64] = {};
+const kyd_ctx* g_scene_owner[2][64] = {};               // [small-scene build, large-scene build of the kernels]
+unsigned long long g_scene_owner_generation[2][64] = {};
 
 int fail(kyd_ctx* ctx, int code, const std::string& msg)
 {
@@ -183,13 +186,15 @@ int bind_scene(kyd_ctx* ctx, cudaStream_t stream)
 {
     std::lock_guard<std::mutex> lock(g_scene_mutex);
     int dev = ctx->device & 63;
-    if (g_scene_owner[dev] != ctx || g_scene_owner_generation[dev] != ctx->scene_generation)
+    const int big = ctx->scene.bvh_nodes != nullptr;
+    if (g_scene_owner[big][dev] != ctx || g_scene_owner_generation[big][dev] != ctx->scene_generation)
     {
         KYD_CUDA(ctx, cudaDeviceSynchronize()); // another context's kernels may still read c_scene
-        upload_scene_constant(ctx->scene, stream);
+        if (big) kyd_big::upload_scene_constant(ctx->scene, stream);
+        else upload_scene_constant(ctx->scene, stream);
         KYD_CUDA(ctx, cudaGetLastError());
-        g_scene_owner[dev] = ctx;
-        g_scene_owner_generation[dev] = ctx->scene_generation;
+        g_scene_owner[big][dev] = ctx;
+        g_scene_owner_generation[big][dev] = ctx->scene_generation;
     }
     return KYD_OK;
 }
@@ -226,12 +231,17 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         const WavefrontPlan plan = wavefront_plan(rp, ctx->scene);
         KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, plan.nee ? ctx->scene.n_lights : 0, plan.split));
         ctx->timer.stream = stream;
-        launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches,
-                                ctx->stage_timing ? &ctx->timer : nullptr);
+        if (ctx->scene.bvh_nodes)
+            kyd_big::launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches,
+                                             ctx->stage_timing ? &ctx->timer : nullptr);
+        else
+            launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches,
+                                    ctx->stage_timing ? &ctx->timer : nullptr);
     }
     else
     {
-        launch_render_pixels(rp, film_dev, ctx->counters_dev, stream);
+        if (ctx->scene.bvh_nodes) kyd_big::launch_render_pixels(rp, film_dev, ctx->counters_dev, stream);
+        else launch_render_pixels(rp, film_dev, ctx->counters_dev, stream);
         launches += 1;
     }
     KYD_CUDA(ctx, cudaGetLastError());
@@ -298,12 +308,14 @@ void kyd_destroy(kyd_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     {
         std::lock_guard<std::mutex> lock(g_scene_mutex);
-        if (g_scene_owner[ctx->device & 63] == ctx) g_scene_owner[ctx->device & 63] = nullptr;
+        for (int b = 0; b < 2; ++b)
+            if (g_scene_owner[b][ctx->device & 63] == ctx) g_scene_owner[b][ctx->device & 63] = nullptr;
     }
     free_wave_buffers(ctx->wave);
     if (ctx->film_dev) cudaFree(ctx->film_dev);
     if (ctx->film_pinned) cudaFreeHost(ctx->film_pinned);
     if (ctx->body_dev) cudaFree(ctx->body_dev);
+    if (ctx->big_scene_dev) cudaFree(ctx->big_scene_dev);
     if (ctx->counters_dev) cudaFree(ctx->counters_dev);
     if (ctx->counters_pinned) cudaFreeHost(ctx->counters_pinned);
     if (ctx->ev_begin) cudaEventDestroy(ctx->ev_begin);
@@ -317,13 +329,147 @@ const char* kyd_last_error(const kyd_ctx* ctx)
     return ctx ? ctx->error.c_str() : g_create_error.c_str();
 }
 
+namespace {
+
+// ---- bounding-volume hierarchy of a large scene (the reference's accel_t is an empty hook, ky.cpp:3097-3115) ----------
+struct Box { float lo[3], hi[3]; };
+
+Box shape_box(const DevShape& s)
+{
+    Box b;
+    const float3 pts[4] = { s.p0, s.p1, s.p2, s.p3 };
+    const int n = s.kind == KYD_SHAPE_RECTANGLE ? 4 : s.kind == KYD_SHAPE_TRIANGLE ? 3 : 1;
+    const float r = (s.kind == KYD_SHAPE_SPHERE || s.kind == KYD_SHAPE_DISK) ? s.radius : 0.f;
+    for (int a = 0; a < 3; ++a)
+    {
+        float lo = 3.4e38f, hi = -3.4e38f;
+        for (int k = 0; k < n; ++k)
+        {
+            const float v = a == 0 ? pts[k].x : a == 1 ? pts[k].y : pts[k].z;
+            lo = v - r < lo ? v - r : lo;
+            hi = v + r > hi ? v + r : hi;
+        }
+        // padding: hits are accepted by the shapes' own arithmetic, whose points may sit a rounding error outside
+        const float m = fabsf(lo) > fabsf(hi) ? fabsf(lo) : fabsf(hi);
+        const float pad = 1e-3f + 1e-4f * m + 1e-3f * (hi - lo);
+        b.lo[a] = lo - pad;
+        b.hi[a] = hi + pad;
+    }
+    return b;
+}
+
+struct BvhBuilder
+{
+    const std::vector<Box>& boxes;
+    std::vector<BvhNode> nodes;
+    std::vector<int> prims;
+
+    explicit BvhBuilder(const std::vector<Box>& b) : boxes(b)
+    {
+        prims.resize(b.size());
+        for (size_t i = 0; i < b.size(); ++i) prims[i] = (int)i;
+        nodes.reserve(2 * b.size());
+        nodes.push_back(BvhNode{});
+        build(0, 0, (int)b.size());
+    }
+
+    void build(int node, int first, int count)
+    {
+        Box bound{ { 3.4e38f, 3.4e38f, 3.4e38f }, { -3.4e38f, -3.4e38f, -3.4e38f } };
+        float clo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, chi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+        for (int k = first; k < first + count; ++k)
+        {
+            const Box& b = boxes[prims[k]];
+            for (int a = 0; a < 3; ++a)
+            {
+                bound.lo[a] = b.lo[a] < bound.lo[a] ? b.lo[a] : bound.lo[a];
+                bound.hi[a] = b.hi[a] > bound.hi[a] ? b.hi[a] : bound.hi[a];
+                const float c = 0.5f * (b.lo[a] + b.hi[a]);
+                clo[a] = c < clo[a] ? c : clo[a];
+                chi[a] = c > chi[a] ? c : chi[a];
+            }
+        }
+        for (int a = 0; a < 3; ++a) { nodes[node].bmin[a] = bound.lo[a]; nodes[node].bmax[a] = bound.hi[a]; }
+        int axis = 0;
+        for (int a = 1; a < 3; ++a)
+            if (chi[a] - clo[a] > chi[axis] - clo[axis]) axis = a;
+        if (count <= 4 || !(chi[axis] > clo[axis]))
+        {
+            nodes[node].left = first;
+            nodes[node].count = count;
+            return;
+        }
+        // median split on the centroids along the widest axis
+        const int mid = first + count / 2;
+        std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count, [&](int x, int y) {
+            return boxes[x].lo[axis] + boxes[x].hi[axis] < boxes[y].lo[axis] + boxes[y].hi[axis];
+        });
+        const int left = (int)nodes.size();
+        nodes.push_back(BvhNode{});
+        nodes.push_back(BvhNode{});
+        nodes[node].left = left;
+        nodes[node].count = 0;
+        build(left, first, mid - first);
+        build(left + 1, mid, first + count - mid);
+    }
+};
+
+// large scene: per-surface data and the hierarchy go to one device allocation; d gets the pointers
+int upload_big_scene(kyd_ctx* ctx, const kyd_scene_desc* sc, DevScene& d)
+{
+    const int n = sc->surface_count;
+    std::vector<DevShape> shapes(n);
+    std::vector<int> materials(n), lights(n);
+    std::vector<Box> boxes(n);
+    for (int i = 0; i < n; ++i)
+    {
+        const kyd_surface& s = sc->surfaces[i];
+        shapes[i] = convert_shape(sc->shapes[s.shape]);
+        materials[i] = s.material;
+        lights[i] = s.area_light;
+        boxes[i] = shape_box(shapes[i]);
+    }
+    BvhBuilder bvh(boxes);
+    auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_shapes = 0, o_mat = align(o_shapes + sizeof(DevShape) * n), o_light = align(o_mat + sizeof(int) * n),
+                 o_nodes = align(o_light + sizeof(int) * n), o_prims = align(o_nodes + sizeof(BvhNode) * bvh.nodes.size()),
+                 total = align(o_prims + sizeof(int) * n);
+    std::vector<unsigned char> host(total, 0);
+    memcpy(host.data() + o_shapes, shapes.data(), sizeof(DevShape) * n);
+    memcpy(host.data() + o_mat, materials.data(), sizeof(int) * n);
+    memcpy(host.data() + o_light, lights.data(), sizeof(int) * n);
+    memcpy(host.data() + o_nodes, bvh.nodes.data(), sizeof(BvhNode) * bvh.nodes.size());
+    memcpy(host.data() + o_prims, bvh.prims.data(), sizeof(int) * n);
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    KYD_CUDA(ctx, cudaDeviceSynchronize());   // kernels of an earlier render may still read the previous scene
+    if (ctx->big_scene_dev) cudaFree(ctx->big_scene_dev);
+    ctx->big_scene_dev = nullptr;
+    KYD_CUDA(ctx, cudaMalloc(&ctx->big_scene_dev, total));
+    KYD_CUDA(ctx, cudaMemcpy(ctx->big_scene_dev, host.data(), total, cudaMemcpyHostToDevice));
+    const char* base = (const char*)ctx->big_scene_dev;
+    d.big_shape = (const DevShape*)(base + o_shapes);
+    d.big_material = (const int*)(base + o_mat);
+    d.big_light = (const int*)(base + o_light);
+    d.bvh_nodes = (const BvhNode*)(base + o_nodes);
+    d.bvh_prims = (const int*)(base + o_prims);
+    for (int l = 0; l < KYD_MAX_LIGHTS; ++l)
+        d.light_surface[l] = -1;
+    for (int i = 0; i < n; ++i)
+        if (lights[i] >= 0)
+            d.light_surface[lights[i]] = d.light_surface[lights[i]] == -1 ? i : -2;
+    return KYD_OK;
+}
+
+} // namespace
+
 int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
 {
     if (!ctx) return KYD_ERR_INVALID;
     if (!sc) return fail(ctx, KYD_ERR_INVALID, "scene desc is null");
-    if (sc->surface_count < 0 || sc->surface_count > KYD_MAX_SURFACES || sc->shape_count < 0 || sc->shape_count > KYD_MAX_SHAPES ||
+    if (sc->surface_count < 0 || sc->surface_count > KYD_MAX_SURFACES_BVH || sc->shape_count < 0 || sc->shape_count > KYD_MAX_SHAPES_BVH ||
         sc->material_count < 0 || sc->material_count > KYD_MAX_MATERIALS || sc->light_count < 0 || sc->light_count > KYD_MAX_LIGHTS)
         return fail(ctx, KYD_ERR_LIMIT, "scene exceeds KYD_MAX_* limits");
+    const bool big = sc->surface_count > KYD_MAX_SURFACES;   // global memory + bounding-volume hierarchy instead of constant memory
 
     DevScene& d = ctx->scene;
     memset(&d, 0, sizeof(d));
@@ -347,10 +493,18 @@ int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
             return fail(ctx, KYD_ERR_INVALID, "surface index out of range");
         if (sc->shapes[s.shape].kind < 0 || sc->shapes[s.shape].kind > KYD_SHAPE_DISK)
             return fail(ctx, KYD_ERR_INVALID, "unknown shape kind");
+        if (big)
+            continue;
         d.surf_shape[i] = convert_shape(sc->shapes[s.shape]);
         d.surf_material[i] = s.material;
         d.surf_light[i] = s.area_light;
     }
+    if (big)
+    {
+        int rc = upload_big_scene(ctx, sc, d);
+        if (rc != KYD_OK) return rc;
+    }
+    else
     {
         // traversal copy grouped by kind; list order inside a group (ties are resolved by surface index, see scene_closest)
         const int group_kind[4] = { KYD_SHAPE_RECTANGLE, KYD_SHAPE_SPHERE, KYD_SHAPE_TRIANGLE, KYD_SHAPE_DISK };

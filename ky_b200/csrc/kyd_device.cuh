@@ -19,7 +19,21 @@
 #include "kyd.h"
 #include "kyd_scene.h"
 
-namespace kyd {
+// The device code is compiled twice: as namespace kyd for scenes in constant memory (kyd_kernels.cu) and, with
+// KYD_BIG_SCENE, as namespace kyd_big for scenes under a bounding-volume hierarchy in global memory
+// (kyd_kernels_big.cu) -- two sets of kernels, so that the headline kernels carry no trace of the other path (run-time
+// hooks inside the traversal cost them 7 %, profiles/r01_ab_variants.txt).
+#ifndef KYD_BIG_SCENE
+#define KYD_BIG_SCENE 0
+#endif
+#if KYD_BIG_SCENE
+#define KYD_KERNEL_NS kyd_big
+namespace kyd_big { using namespace kyd; }
+#else
+#define KYD_KERNEL_NS kyd
+#endif
+
+namespace KYD_KERNEL_NS {
 
 #define KYD_DEV __device__ __forceinline__
 // the double-precision libm bodies are hundreds of instructions each and have many call sites: kept out of
@@ -778,6 +792,18 @@ KYD_DEV void material_scattering(const DevMaterial& m, const HitGeom& g, Bsdf* b
     }
 }
 
+// ---- per-surface data: constant memory, or global memory for a large scene -----------------------------------
+// (KYD_BIG_SCENE: this translation unit is the large-scene build of the kernels, kyd_kernels_big.cu)
+#if KYD_BIG_SCENE
+KYD_DEV const DevShape& surface_shape(int i) { return c_scene.big_shape[i]; }
+KYD_DEV int surface_material(int i) { return c_scene.big_material[i]; }
+KYD_DEV int surface_light(int i) { return c_scene.big_light[i]; }
+#else
+KYD_DEV const DevShape& surface_shape(int i) { return c_scene.surf_shape[i]; }
+KYD_DEV int surface_material(int i) { return c_scene.surf_material[i]; }
+KYD_DEV int surface_light(int i) { return c_scene.surf_light[i]; }
+#endif
+
 // ---- scene traversal ky.cpp:3077-3088, 3172-3206 ------------------------------------------------------------
 
 // The distance at which shape_t::intersect would report a hit if tmax were unbounded: the same arithmetic and the
@@ -840,6 +866,98 @@ KYD_DEV bool shape_hit_candidate(const DevShape& s, const Ray& r, float* out_t)
     }
 }
 
+#if KYD_BIG_SCENE
+// ---- large scenes: the same three queries over a bounding-volume hierarchy in global memory ----------------------
+// Any visiting order gives the linear walk's answer as long as no box is skipped that holds a qualifying hit and ties
+// follow the list order: boxes are padded at upload, the slab test rejects only intervals that are empty by a margin,
+// and a node is skipped for distance only if it starts strictly beyond the current best (equal distances must be seen:
+// the lower surface index wins).
+KYD_DEV bool shape_hit_candidate_any_kind(const DevShape& s, const Ray& r, float* out_t)
+{
+    switch (s.kind)
+    {
+    case KYD_SHAPE_SPHERE: return shape_hit_candidate<KYD_SHAPE_SPHERE>(s, r, out_t);
+    case KYD_SHAPE_RECTANGLE: return shape_hit_candidate<KYD_SHAPE_RECTANGLE>(s, r, out_t);
+    case KYD_SHAPE_TRIANGLE: return shape_hit_candidate<KYD_SHAPE_TRIANGLE>(s, r, out_t);
+    default: return shape_hit_candidate<KYD_SHAPE_DISK>(s, r, out_t);
+    }
+}
+
+// entry distance of the ray into the node's box, or a negative value if it misses the box within [0, limit]
+KYD_DEV float bvh_box_entry(const BvhNode& n, float3 o, float3 inv_d, float limit)
+{
+    // fminf / fmaxf drop NaNs (0 * inf when the origin lies on a slab plane of an axis the ray is parallel to)
+    float t0 = 0.f, t1 = limit;
+    const float ax = (n.bmin[0] - o.x) * inv_d.x, bx = (n.bmax[0] - o.x) * inv_d.x;
+    t0 = fmaxf(t0, fminf(ax, bx)); t1 = fminf(t1, fmaxf(ax, bx));
+    const float ay = (n.bmin[1] - o.y) * inv_d.y, by = (n.bmax[1] - o.y) * inv_d.y;
+    t0 = fmaxf(t0, fminf(ay, by)); t1 = fminf(t1, fmaxf(ay, by));
+    const float az = (n.bmin[2] - o.z) * inv_d.z, bz = (n.bmax[2] - o.z) * inv_d.z;
+    t0 = fmaxf(t0, fminf(az, bz)); t1 = fminf(t1, fmaxf(az, bz));
+    return t0 <= t1 * 1.0001f + 1e-4f ? t0 : -1.f;
+}
+
+#define KYD_BVH_STACK 48
+
+// MODE 0: closest hit (returns the surface, *out_t the distance); MODE 1: any hit inside (epsilon, r.tmax) (returns 0 / -1);
+// MODE 2: any surface other than `light_surface` before it, r.tmax = its distance (returns 0 / -1)
+template <int MODE>
+__device__ __noinline__ int bvh_query(Ray r, int light_surface, float* out_t)
+{
+    const float3 inv_d = V3(1.f / r.d.x, 1.f / r.d.y, 1.f / r.d.z);
+    float tmax = r.tmax;
+    int best = -1;
+    int stack[KYD_BVH_STACK];
+    int top = 0;
+    stack[top++] = 0;
+    while (top > 0)
+    {
+        const BvhNode node = c_scene.bvh_nodes[stack[--top]];
+        const float entry = bvh_box_entry(node, r.o, inv_d, tmax);
+        if (entry < 0.f)
+            continue;
+        if (node.count == 0)
+        {
+            if (top + 2 <= KYD_BVH_STACK)
+            {
+                stack[top++] = node.left + 1;
+                stack[top++] = node.left;
+            }
+            continue;
+        }
+        for (int k = 0; k < node.count; ++k)
+        {
+            const int surface = c_scene.bvh_prims[node.left + k];
+            float t;
+            if (!shape_hit_candidate_any_kind(c_scene.big_shape[surface], r, &t))
+                continue;
+            if (MODE == 0)
+            {
+                if (t < tmax || (t == tmax && surface < best))
+                {
+                    tmax = t;
+                    best = surface;
+                }
+            }
+            else if (MODE == 1)
+            {
+                if (t < r.tmax)
+                    return 0;
+            }
+            else
+            {
+                if (surface != light_surface && (t < r.tmax || (t == r.tmax && surface < light_surface)))
+                    return 0;
+            }
+        }
+    }
+    if (MODE == 0)
+        *out_t = tmax;
+    return best;
+}
+
+#endif // KYD_BIG_SCENE
+
 // One loop per shape kind over the kind-sorted copy of the surface list: no per-surface dispatch, and the loop
 // counter, the bounds and the shape data stay warp-uniform (uniform-datapath constant loads).  The reference walks
 // the list in order with a strict `t < tmax` (ky.cpp:3172-3184), i.e. the closest hit, the LOWEST surface index among
@@ -865,6 +983,9 @@ KYD_DEV void scene_closest_kind(const Ray& r, float& tmax, int& best)
 
 KYD_DEV int scene_closest(const Ray& r, float* out_t)
 {
+#if KYD_BIG_SCENE
+    return bvh_query<0>(r, -1, out_t);
+#endif
     float tmax = r.tmax;
     int best = -1;
     scene_closest_kind<0, KYD_SHAPE_RECTANGLE>(r, tmax, best);
@@ -891,6 +1012,9 @@ KYD_DEV bool scene_any_hit_kind(const Ray& r)
 // scene_t::occluded's question (ky.cpp:3187-3206): is any surface hit inside (epsilon, tmax)?  Order-independent.
 KYD_DEV bool scene_any_hit(const Ray& r)
 {
+#if KYD_BIG_SCENE
+    return r.tmax > KYD_SHAPE_EPSILON && bvh_query<1>(r, -1, nullptr) == 0;
+#endif
     return scene_any_hit_kind<0, KYD_SHAPE_RECTANGLE>(r) || scene_any_hit_kind<1, KYD_SHAPE_SPHERE>(r) ||
            scene_any_hit_kind<2, KYD_SHAPE_TRIANGLE>(r) || scene_any_hit_kind<3, KYD_SHAPE_DISK>(r);
 }
@@ -917,6 +1041,9 @@ KYD_DEV bool scene_blocked_before_kind(const Ray& r, int light_surface)
 
 KYD_DEV bool scene_blocked_before(const Ray& r, int light_surface)
 {
+#if KYD_BIG_SCENE
+    return bvh_query<2>(r, light_surface, nullptr) == 0;
+#endif
     return scene_blocked_before_kind<0, KYD_SHAPE_RECTANGLE>(r, light_surface) || scene_blocked_before_kind<1, KYD_SHAPE_SPHERE>(r, light_surface) ||
            scene_blocked_before_kind<2, KYD_SHAPE_TRIANGLE>(r, light_surface) || scene_blocked_before_kind<3, KYD_SHAPE_DISK>(r, light_surface);
 }
@@ -941,6 +1068,9 @@ KYD_DEV bool scene_blocked_before_kind_uniform(const Ray& r, int light_surface, 
 
 KYD_DEV bool scene_blocked_before_uniform(const Ray& r, int light_surface)
 {
+#if KYD_BIG_SCENE
+    return light_surface >= 0 && bvh_query<2>(r, light_surface, nullptr) == 0;
+#endif
     const bool idle = light_surface < 0;
     bool done = idle;
     done = scene_blocked_before_kind_uniform<0, KYD_SHAPE_RECTANGLE>(r, light_surface, done);
@@ -970,6 +1100,9 @@ KYD_DEV bool scene_any_hit_kind_uniform(const Ray& r, bool hit)
 
 KYD_DEV bool scene_any_hit_uniform(const Ray& r)
 {
+#if KYD_BIG_SCENE
+    return r.tmax > KYD_SHAPE_EPSILON && bvh_query<1>(r, -1, nullptr) == 0;
+#endif
     bool hit = !(r.tmax > KYD_SHAPE_EPSILON);   // nothing lies in (epsilon, tmax): answered (the caller ignores it)
     if (__all_sync(0xffffffffu, hit)) return false;
     hit = scene_any_hit_kind_uniform<0, KYD_SHAPE_RECTANGLE>(r, hit);
@@ -988,7 +1121,7 @@ KYD_DEV float3 areal_radiance(const DevLight& l, float3 light_normal, float3 wo)
 
 KYD_DEV float3 surface_emission(int surface, const HitGeom& g) // ky.cpp:3084
 {
-    int li = c_scene.surf_light[surface];
+    int li = surface_light(surface);
     return li >= 0 ? areal_radiance(c_scene.lights[li], g.normal, g.wo) : KYD_BLACK;
 }
 
@@ -1140,9 +1273,10 @@ KYD_DEV NeeRay nee_bsdf_setup(const HitGeom& g, const Bsdf& b, int light_index, 
         if (ls < 0)
             return q;   // no surface carries the light: whatever the ray hits, it is not this light
         float t_light;
-        if (!shape_hit_distance(c_scene.surf_shape[ls], q.ray, KYD_INF, &t_light))
+        const DevShape& light_surface_shape = surface_shape(ls);
+        if (!shape_hit_distance(light_surface_shape, q.ray, KYD_INF, &t_light))
             return q;
-        HitGeom lg = shape_hit_geom(c_scene.surf_shape[ls], q.ray, t_light);
+        HitGeom lg = shape_hit_geom(light_surface_shape, q.ray, t_light);
         if (!(dot(lg.normal, lg.wo) > 0))
             return q;   // areal_radiance is one-sided (ky.cpp:2957-2960)
         q.light_surface = ls;
@@ -1167,10 +1301,10 @@ KYD_DEV float3 nee_bsdf_resolve(const NeeRay& q, int hit_surface, float hit_t)
     const DevLight& l = c_scene.lights[q.light];
     if (hit_surface >= 0)
     {
-        if (c_scene.surf_light[hit_surface] != q.light)
+        if (surface_light(hit_surface) != q.light)
             return KYD_BLACK;
         // emission of the hit: areal_radiance(light_isect, light_isect.wo) with the hit's normal
-        HitGeom lg = shape_hit_geom(c_scene.surf_shape[hit_surface], q.ray, hit_t);
+        HitGeom lg = shape_hit_geom(surface_shape(hit_surface), q.ray, hit_t);
         return (dot(lg.normal, lg.wo) > 0) ? q.value : KYD_BLACK;
     }
     return l.kind == KYD_LIGHT_ENVIRONMENT ? q.value : KYD_BLACK;
@@ -1243,4 +1377,4 @@ KYD_DEV Ray generate_ray(float px, float py)
     return r;
 }
 
-} // namespace kyd
+} // namespace KYD_KERNEL_NS

@@ -82,7 +82,8 @@ inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scen
     WavefrontPlan p;
     const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
     p.split = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) != 0;
-    p.hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG && !p.split;
+    // (large scenes run the general kernels only: the specialised ones are not built for them)
+    p.hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG && !p.split && scene.bvh_nodes == nullptr;
     p.inline_queries = p.hot && scene.n_lights == 1;
     p.nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0 && !p.inline_queries;
     return p;
@@ -98,3 +99,11 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                              cudaStream_t stream, int sm_count, uint64_t* launches, StageTimer* timer);
 
 } // namespace kyd
+
+// the large-scene build of the kernels (kyd_kernels_big.cu): same entry points over a scene in global memory + BVH
+namespace kyd_big {
+void upload_scene_constant(const kyd::DevScene& scene, cudaStream_t stream);
+void launch_render_pixels(const kyd::RenderParams& rp, float* film_dev, kyd::DevCounters* counters, cudaStream_t stream);
+void launch_render_wavefront(const kyd::RenderParams& rp, const kyd::DevScene& scene, kyd::WaveBuffers& w, int64_t wave_paths, float* film_dev,
+                             kyd::DevCounters* counters, cudaStream_t stream, int sm_count, uint64_t* launches, kyd::StageTimer* timer);
+} // namespace kyd_big

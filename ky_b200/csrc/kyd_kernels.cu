@@ -6,7 +6,7 @@
 #include "kyd_device.cuh"
 #include "kyd_wavefront.cuh"
 
-namespace kyd {
+namespace KYD_KERNEL_NS {
 
 void upload_scene_constant(const DevScene& scene, cudaStream_t stream)
 {
@@ -34,8 +34,8 @@ KYD_DEV bool scene_intersect(const Ray& r, Isect& is, Counters& c)
     if (s < 0)
         return false;
     is.surface = s;
-    is.g = shape_hit_geom(c_scene.surf_shape[s], r, t);
-    material_scattering(c_scene.materials[c_scene.surf_material[s]], is.g, &is.b);
+    is.g = shape_hit_geom(surface_shape(s), r, t);
+    material_scattering(c_scene.materials[surface_material(s)], is.g, &is.b);
     is.emission = surface_emission(s, is.g);
     return true;
 }
@@ -49,7 +49,7 @@ KYD_DEV float3 trace_emission(const Ray& r, Counters& c)
     int s = scene_closest(r, &t);
     if (s < 0)
         return environment_lighting();
-    HitGeom g = shape_hit_geom(c_scene.surf_shape[s], r, t);
+    HitGeom g = shape_hit_geom(surface_shape(s), r, t);
     return surface_emission(s, g);
 }
 
@@ -370,6 +370,7 @@ void launch_render_pixels(const RenderParams& rp, float* film_dev, DevCounters* 
     }
 }
 
+#if !KYD_BIG_SCENE // host-side pieces shared by both builds of the kernels live in the small-scene build only
 __global__ void k_clamp(float* __restrict__ film, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -535,6 +536,8 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool v
     return cudaSuccess;
 }
 
+#endif // !KYD_BIG_SCENE
+
 // the mirror and glass kernels sample no lights: one instantiation serves both light counts
 template <int TRAITS, bool HOT, int NL>
 static void launch_shade_lobes(int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
@@ -550,6 +553,7 @@ static void launch_shade(int traits, bool hot, bool one_light, int grid, cudaStr
                          DevCounters* counters, int bounce)
 {
     if (!hot) launch_shade_lobes<TRAITS_ANY, false, NL_ANY>(grid, stream, wp, w, counters, bounce);
+#if !KYD_BIG_SCENE
     else if (traits == TRAITS_AREA_RECTANGLE) launch_shade_lobes<TRAITS_AREA_RECTANGLE, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
     else if (traits == TRAITS_AREA_SPHERE)
     {
@@ -561,6 +565,7 @@ static void launch_shade(int traits, bool hot, bool one_light, int grid, cudaStr
         if (one_light) launch_shade_lobes<TRAITS_ANY, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
         else launch_shade_lobes<TRAITS_ANY, true, NL_MANY>(grid, stream, wp, w, counters, bounce);
     }
+#endif
 }
 
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,
@@ -664,4 +669,4 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     }
 }
 
-} // namespace kyd
+} // namespace KYD_KERNEL_NS

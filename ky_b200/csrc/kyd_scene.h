@@ -43,6 +43,16 @@ struct DevCamera
     float res_x, res_y, push;
 };
 
+// node of the bounding-volume hierarchy of a large scene: an inner node's children are nodes[left] and nodes[left + 1];
+// a leaf (count > 0) covers bvh_prims[left .. left + count)
+struct BvhNode
+{
+    float bmin[3];
+    int left;
+    float bmax[3];
+    int count;
+};
+
 struct DevScene
 {
     DevCamera camera;
@@ -61,6 +71,13 @@ struct DevScene
     DevShape sorted_shape[KYD_MAX_SURFACES];
     int sorted_surface[KYD_MAX_SURFACES];   // surface index of sorted_shape[k]
     int kind_end[4];                        // sorted_shape[kind_end[g-1] .. kind_end[g]) is group g
+    // large scenes (more than KYD_MAX_SURFACES surfaces): per-surface data and the hierarchy in global memory, the arrays
+    // above unused; null pointers otherwise
+    const DevShape* big_shape;
+    const int* big_material;
+    const int* big_light;
+    const BvhNode* bvh_nodes;
+    const int* bvh_prims;                   // surface indices in leaf order
 };
 
 struct RenderParams

@@ -43,7 +43,7 @@
 #include "kyd_device.cuh"
 #include "kyd_internal.h"
 
-namespace kyd {
+namespace KYD_KERNEL_NS {
 
 // queue tails in DevCounters::queue
 enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong): vertices, split light-sample stage only */,
@@ -64,9 +64,9 @@ enum { N_LIGHT_O = 0, N_LIGHT_D = 1, N_LIGHT_VALUE = 2, N_MIXED = 3, N_BSDF_O = 
 enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_BETA = 5, VERTEX_UNITS = 6 };
 
 // flags word of a path (w of the direction unit)
-// bit 0: previous vertex was specular; bits 4-11: 1 + hit surface; bits 16-31: lights whose estimator value is pending
+// bit 0: previous vertex was specular; bits 4-15: 1 + hit surface; bits 16-31: lights whose estimator value is pending
 // (a light-sampling line was written for them at the previous vertex and the shadow stage resolves it)
-enum { FLAG_PREV_SPECULAR = 1, FLAG_SURFACE_SHIFT = 4, FLAG_SURFACE_MASK = 0xff << 4, FLAG_PENDING_SHIFT = 16, FLAG_PENDING_MASK = (int)0xffff0000u };
+enum { FLAG_PREV_SPECULAR = 1, FLAG_SURFACE_SHIFT = 4, FLAG_SURFACE_MASK = 0xfff << 4, FLAG_PENDING_SHIFT = 16, FLAG_PENDING_MASK = (int)0xffff0000u };
 // entry of the pair queues: path slot | light << 24 (a wave holds at most 2^24 paths, a scene at most 16 lights)
 enum { PAIR_LIGHT_SHIFT = 24, PAIR_SLOT_MASK = (1 << 24) - 1 };
 // flags word of a light-sampling line (w of the light query's direction unit)
@@ -264,7 +264,7 @@ KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsi
 // the lobe material_t::scattering will build for this hit (ky.cpp:2587-2671); pure function of the hit
 KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 {
-    const DevMaterial& m = c_scene.materials[c_scene.surf_material[surface]];
+    const DevMaterial& m = c_scene.materials[surface_material(surface)];
     if (m.kind == KYD_MAT_MATTE) return LOBE_LAMBERT;
     if (m.kind == KYD_MAT_MIRROR) return LOBE_MIRROR;
     if (m.kind == KYD_MAT_GLASS) return LOBE_FRESNEL;
@@ -495,7 +495,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
     unsigned new_pending = 0;   // lights that get a light-sampling line at this vertex
 
-    HitGeom g = shape_hit_geom(c_scene.surf_shape[surface], r, st.t);
+    HitGeom g = shape_hit_geom(surface_shape(surface), r, st.t);
 
     if (bounce == 0 || (st.flags & FLAG_PREV_SPECULAR))
         Lo = add(Lo, cmulc(beta, surface_emission(surface, g)));
@@ -505,7 +505,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     unsigned long long rng_state = st.rng;
     if (bounce < wp.rp.max_depth + (direct_only ? 1 : 0))
     {
-        const DevMaterial& m = c_scene.materials[c_scene.surf_material[surface]];
+        const DevMaterial& m = c_scene.materials[surface_material(surface)];
         Bsdf b;
         b.f = frame_from_z(g.normal);
         b.t = KYD_BLACK;
@@ -923,4 +923,4 @@ __global__ void k_zero(float* __restrict__ p, long long n)
         p[i] = 0.f;
 }
 
-} // namespace kyd
+} // namespace KYD_KERNEL_NS

@@ -21,7 +21,7 @@ os.makedirs(os.path.join(g.LIB, "ab"), exist_ok=True)
 procs = []
 for n in names:
     out = os.path.join(g.LIB, "ab", f"libkyd_{n}.so")
-    cmd = ["nvcc"] + g.NVCC_FLAGS + variants[n] + ["-shared", "-o", out, os.path.join(g.CSRC, "kyd_kernels.cu"), os.path.join(g.CSRC, "kyd_api.cu"), os.path.join(g.CSRC, "kyd_film.cu"), os.path.join(g.CSRC, "kyd_smallpt.cu"), "-Xptxas", "-v"]
+    cmd = ["nvcc"] + g.NVCC_FLAGS + variants[n] + ["-shared", "-o", out, os.path.join(g.CSRC, "kyd_kernels.cu"), os.path.join(g.CSRC, "kyd_kernels_big.cu"), os.path.join(g.CSRC, "kyd_api.cu"), os.path.join(g.CSRC, "kyd_film.cu"), os.path.join(g.CSRC, "kyd_smallpt.cu"), "-Xptxas", "-v"]
     procs.append((n, subprocess.Popen(cmd, cwd=g.ROOT, stderr=open(os.path.join(g.LIB, "ab", f"{n}.ptxas.log"), "w"))))
 for n, p in procs:
     print(n, "rc", p.wait())

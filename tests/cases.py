@@ -171,3 +171,42 @@ def trapezoidal_cases():
             ("trap/cornell/direct", "cornell", ky.INT_DIRECT_LIGHTING, ky.DS_LIGHT_MIS, 0, 4),
             ("trap/shapes/normal", "shapes", ky.INT_NORMAL, ky.DS_BOTH_MIS, 0, 4),
             ("trap/cornell/recursion", "cornell", ky.INT_PT_RECURSION, ky.DS_BOTH_MIS, 3, 4)]
+
+
+def big_scene(extra=360, seed=3):
+    """Cornell box + `extra` small spheres / triangles / rectangles / disks scattered inside it (matte, mirror, glass and
+    plastic): more surfaces than constant memory holds (KYD_MAX_SURFACES), so the device walks its bounding-volume
+    hierarchy while the oracle walks the list.  Shapes are built by the host classes' constructors (ky.describe_shape)."""
+    import numpy as np
+    import ky_b200 as ky
+    base = make_scene("cornell")
+    shapes, materials, lights, surfaces = base.shapes, base.materials, base.lights, base.surfaces
+    rng = np.random.default_rng(seed)
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    n_mat = len(materials)
+    for kind, params in ((0, [0.7, 0.6, 0.2, 0, 0, 0, 0]), (1, [0.9, 0.9, 0.9, 0, 0, 0, 0]), (2, [1, 1, 1, 1, 1, 1, 1.5]),
+                         (3, [0.2, 0.3, 0.1, 0.6, 0.6, 0.6, 90])):
+        materials = materials + [ky.describe_material(kind, params)]
+    for k in range(extra):
+        c = rng.uniform([40, 30, 40], [510, 500, 520])
+        size = rng.uniform(6, 28)
+        kind = int(rng.integers(0, 4))
+        if kind == ky.SHAPE_SPHERE:
+            params = [*c, size]
+        elif kind == ky.SHAPE_DISK:
+            params = [*c, *unit(rng.normal(size=3)), size]
+        else:
+            u = unit(rng.normal(size=3)) * size
+            v = unit(np.cross(u, rng.normal(size=3))) * size * rng.uniform(0.5, 1.5)
+            if kind == ky.SHAPE_TRIANGLE:
+                params = [*c, *(c + u), *(c + v), float(k % 2)]
+            else:
+                params = [*c, *(c + u), *(c + u + v), *(c + v), float(k % 2)]
+        sf = ky.Surface()
+        sf.shape, sf.material, sf.area_light = len(shapes), n_mat + int(rng.integers(0, 4)), -1
+        shapes = shapes + [ky.describe_shape(kind, params)]
+        surfaces = surfaces + [sf]
+    return CustomScene(base, shapes, materials, lights, surfaces, base.desc.environment_light)
