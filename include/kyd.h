@@ -228,7 +228,8 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out);
 enum kyd_selftest_kind { KYD_SELFTEST_RSQRT = 0, KYD_SELFTEST_POW = 1 };
 int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2);
 
-/* size in paths of one wavefront (0 = choose from the film size); tuning knob, results do not depend on it */
+/* size in paths of one wavefront (0 = library default, 2^24; larger values are clamped to 2^24); tuning knob, results do
+   not depend on it */
 int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths);
 
 /* ---- film output stage: the step right after the path (replaces the per-pixel loops of
