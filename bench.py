@@ -33,6 +33,8 @@ SM_COUNT, LANES_PER_SM = 148, 128
 STAGES = ["raygen", "intersect", "shade", "light_sample", "shadow", "-", "accumulate", "pixel"]
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_shade<Lambert> launch (ncu --set full, profiles/r01_final_kernels.txt)
 NCU_SHADE_TRAFFIC = 768990208  # bytes, k_shade<Lambert> of bounce 1 of a 16.6 M-path wave
+# smsp__issue_active.avg.pct_of_peak_sustained_active of the same capture (profiles/r01_final_kernels.txt)
+NCU_ISSUE_ACTIVE = {"k_intersect": 0.81, "k_shade<Lambert>": 0.59, "k_shade<Phong>": 0.40, "source": "profiles/r01_final_kernels.txt"}
 
 
 def JOB_WAVES(spp_per_step, capacity=1 << 24):
@@ -332,7 +334,9 @@ def main():
             "roofline_fp32_issue": {"achieved": achieved_flops / 1e12, "peak": peak_lane_ops / 1e12, "unit": "TFLOP/s (FP32 lane-ops/s, FMA off)",
                                     "frac": achieved_flops / peak_lane_ops,
                                     "note": f"whole step: {FLOP_PER_RAY} flop/ray x reference-equivalent rays, per GPU; peak = {SM_COUNT} SMs x {LANES_PER_SM} lanes x "
-                                            f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} max SM clock; median under load {sm_mhz}); tensor cores unused"},
+                                            f"{peaks['sm_max_mhz']:.0f} MHz ({peaks['source']} max SM clock; median under load {sm_mhz}); tensor cores unused",
+                                    # issue-slot utilisation of the kernels themselves, from the ncu capture of this build
+                                    "issue_active_ncu": NCU_ISSUE_ACTIVE},
         }
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference()
