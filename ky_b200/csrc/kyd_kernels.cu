@@ -2,6 +2,7 @@
 // the clamp kernel.  The wavefront stages live in kyd_wavefront.cu.
 //
 // Compile with -fmad=false (see kyd_device.cuh).
+#include <cstdlib>
 #include "kyd_internal.h"
 #include "kyd_device.cuh"
 #include "kyd_wavefront.cuh"
@@ -594,7 +595,10 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     }
 
     // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
-    const int grid256 = sm_count * 16, grid128 = sm_count * 24;
+    // (blocks per SM; measured flat between 8 and 24, profiles/r01_ab_variants.txt; KYD_GRID256 / KYD_GRID128 override them for experiments)
+    static const int grid256_per_sm = getenv("KYD_GRID256") ? atoi(getenv("KYD_GRID256")) : 16;
+    static const int grid128_per_sm = getenv("KYD_GRID128") ? atoi(getenv("KYD_GRID128")) : 24;
+    const int grid256 = sm_count * grid256_per_sm, grid128 = sm_count * grid128_per_sm;
 
     if (!(rp.flags & KYD_FLAG_ACCUMULATE))
     {
