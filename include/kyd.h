@@ -224,7 +224,7 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out);
    the `count` float bit patterns starting at `first`; out2[0] = mismatches, out2[1] = inputs that took the slow path.
    KYD_SELFTEST_POW: compares powf's fast path (exp2(y log2 x) + rounding-interval check) with its definition
    (float)pow((double)x, (double)y) on `count` argument pairs derived from the indices first.. (Phong's exponents
-   30 / 90 / 5000 and their 1/(n+1), random exponents; bases dense next to 1) */
+   30 / 90 / 5000 and their 1/(n+1), random exponents; bases dense next to 1; negative bases with integer exponents) */
 enum kyd_selftest_kind { KYD_SELFTEST_RSQRT = 0, KYD_SELFTEST_POW = 1 };
 int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2);
 

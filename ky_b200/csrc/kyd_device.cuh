@@ -86,16 +86,25 @@ KYD_MATH float cr_pow_reference(float x, float y) { return __double2float_rn(pow
 // double is within 2^-45 of x^y when |y log2 x| < 120 (log2 and exp2 are 1-ulp functions; the product's error is
 // 2^-52 |y log2 x|), the definition's double pow is within 2^-52 of it; if v sits at least 2^-41 (relative) inside
 // its float rounding interval both round to the same float.  Results below 2^-160 round to +0 either way.
-// Everything else -- x <= 0, non-finite or huge arguments, denormal results, values too close to a rounding
+// A negative base with an integer exponent -- Phong's eval takes powf of a negative cosine (ky.cpp:2496-2499; its exponents
+// 30 / 90 / 5000 are integers) -- is (-1)^y |x|^y, exactly and with symmetric rounding, so it takes the same path.
+// Everything else -- zero, non-finite or huge arguments, denormal results, values too close to a rounding
 // boundary (2^-15 of calls) -- evaluates the definition.  tests: kyd_selftest(KYD_SELFTEST_POW).
 KYD_DEV float cr_pow(float x, float y)
 {
 #if !defined(KYD_FAST_POW) || KYD_FAST_POW
-    if (x > 0x1p-100f && x < 0x1p100f && fabsf(y) < 1e6f)
+    float ax = x;
+    bool negate = false;
+    if (x < 0.f && fabsf(y) < 1e6f && y == truncf(y))
     {
-        const double t = (double)y * log2((double)x);
+        ax = -x;
+        negate = (__float2int_rz(y) & 1) != 0;
+    }
+    if (ax > 0x1p-100f && ax < 0x1p100f && fabsf(y) < 1e6f)
+    {
+        const double t = (double)y * log2((double)ax);
         if (t < -160.0)
-            return 0.f;
+            return negate ? -0.f : 0.f;
         if (fabs(t) < 120.0)
         {
             const double v = exp2(t);
@@ -106,7 +115,7 @@ KYD_DEV float cr_pow(float x, float y)
             const double hi = half_ulp * (1.0 - 0x1p-16);
             const double lo = (fb & 0x007fffffu) != 0u ? -hi : -0.5 * hi;
             if (d < hi && d > lo)
-                return f;
+                return negate ? -f : f;
         }
     }
 #endif

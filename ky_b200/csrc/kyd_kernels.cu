@@ -427,16 +427,18 @@ __global__ void k_selftest_pow(unsigned long long first, unsigned long long coun
         const float ys[6] = { 90.f, 5000.f, 30.f, 1.f / 91.f, 1.f / 5001.f, 1.f / 31.f };
         if (k < 6) { y = ys[k]; x = k < 3 ? 1.f - u * v * 0.05f : u; }
         else if (k < 12) { y = ys[k - 6]; x = k < 9 ? 1.f - u * u * u : u * v; }
-        else { y = (v * 2.f - 1.f) * 100.f; x = u * 4.f; }
+        else if (k < 14) { y = (v * 2.f - 1.f) * 100.f; x = u * 4.f; }
+        else { y = ys[(h >> 8) % 3]; x = k == 14 ? -(u * v) : -(1.f - u * v * 0.05f); }   // negative base, integer exponent
         const float want = cr_pow_reference(x, y);
         const float got = cr_pow(x, y);
         if (__float_as_uint(want) != __float_as_uint(got) && !(want != want && got != got))
             ++bad;
         // a second evaluation of the fast path's conditions to count how often the definition was needed
         bool fast = false;
-        if (x > 0x1p-100f && x < 0x1p100f && fabsf(y) < 1e6f)
+        const float ax = (x < 0.f && y == truncf(y)) ? -x : x;
+        if (ax > 0x1p-100f && ax < 0x1p100f && fabsf(y) < 1e6f)
         {
-            const double t = (double)y * log2((double)x);
+            const double t = (double)y * log2((double)ax);
             fast = t < -160.0 || fabs(t) < 120.0;
         }
         if (!fast) ++slow;
