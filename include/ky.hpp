@@ -422,12 +422,17 @@ private:
 class device_t
 {
 public:
+    // The process-wide device context behind integrator_t::render.  Which GPUs it spans is the environment's choice, so
+    // that unchanged ky code scales: KY_CUDA_DEVICES = "all" or a comma-separated list of CUDA ordinals ("0,1,2,3")
+    // makes it a multi-GPU context (kyd_create_multi: the samples of every render are split over the devices and the
+    // partial films summed on the first); otherwise it is the single device KY_CUDA_DEVICE (default 0).
     static device_t& instance(int cuda_device = -1)
     {
-        static device_t dev(cuda_device < 0 ? env_device() : cuda_device);
+        static device_t dev(cuda_device < 0 ? env_devices() : std::vector<int>{ cuda_device });
         return dev;
     }
     kyd_ctx* ctx() const { return ctx_; }
+    int device_count() const { return kyd_device_count(ctx_); }
     void check(int rc) const
     {
         if (rc != KYD_OK)
@@ -436,15 +441,47 @@ public:
     ~device_t() { kyd_destroy(ctx_); }
 
 private:
-    explicit device_t(int cuda_device)
+    explicit device_t(const std::vector<int>& devices)
     {
-        if (kyd_create(&ctx_, cuda_device) != KYD_OK)
+        const int rc = devices.size() == 1 ? kyd_create(&ctx_, devices[0]) : kyd_create_multi(&ctx_, devices.data(), (int)devices.size());
+        if (rc != KYD_OK)
             throw std::runtime_error(std::string("kyd_create: ") + kyd_last_error(nullptr));
     }
-    static int env_device()
+    static std::vector<int> env_devices()
     {
-        const char* e = std::getenv("KY_CUDA_DEVICE");
-        return e ? std::atoi(e) : 0;
+        std::vector<int> out;
+        if (const char* list = std::getenv("KY_CUDA_DEVICES"))
+        {
+            const std::string s(list);
+            if (s == "all")
+            {
+                // probe by creating contexts until an ordinal is refused
+                for (int d = 0; d < KYD_MAX_MULTI; ++d)
+                {
+                    kyd_ctx* probe = nullptr;
+                    if (kyd_create(&probe, d) != KYD_OK) break;
+                    kyd_destroy(probe);
+                    out.push_back(d);
+                }
+            }
+            else
+            {
+                size_t pos = 0;
+                while (pos < s.size())
+                {
+                    size_t comma = s.find(',', pos);
+                    if (comma == std::string::npos) comma = s.size();
+                    if (comma > pos) out.push_back(std::atoi(s.substr(pos, comma - pos).c_str()));
+                    pos = comma + 1;
+                }
+            }
+        }
+        if (out.empty())
+        {
+            const char* e = std::getenv("KY_CUDA_DEVICE");
+            out.push_back(e ? std::atoi(e) : 0);
+        }
+        return out;
     }
     kyd_ctx* ctx_{};
 };

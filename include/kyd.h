@@ -197,8 +197,22 @@ typedef struct kyd_stats
 
 typedef struct kyd_ctx kyd_ctx;
 
-/* creates a context on CUDA device `device` (cudaSetDevice ordinal) with its own stream */
+/* creates a context on CUDA device `device` (cudaSetDevice ordinal) with its own stream.  The stream is a blocking one:
+   work queued on the device's legacy default stream before a call is complete before the call's kernels run. */
 int kyd_create(kyd_ctx** out_ctx, int device);
+
+/* Multi-GPU context behind the same calls: `devices` lists n CUDA ordinals (1..KYD_MAX_MULTI; an
+   ordinal may repeat).  kyd_upload_scene copies the scene to every device; kyd_render / kyd_render_device split the
+   sample range [sample_begin, sample_end) evenly over the devices (every device renders its sample indices of EVERY
+   pixel into an unclamped partial film, one host thread per device), the partial films are added on devices[0] in rank
+   order by one kernel that reads the peers' films over their NVLink peer mappings, and KYD_FLAG_CLAMP is applied after
+   that sum -- the reference clamps after the spp-sum (ky.cpp:3721-3726).  The film pointer of kyd_render_device lives
+   on devices[0].  The re-associated per-pixel sum differs from the single-device film by rounding only (<= ~1e-6
+   relative) and is the same from run to run.  kyd_get_stats reports sums over the devices (device_ms: devices[0]'s
+   interval, which ends behind the final sum).  Everything else (film stage, self-tests) runs on devices[0]. */
+enum { KYD_MAX_MULTI = 16 };
+int kyd_create_multi(kyd_ctx** out_ctx, const int* devices, int n);
+int kyd_device_count(const kyd_ctx* ctx);   /* devices behind the context (1 for kyd_create) */
 void kyd_destroy(kyd_ctx* ctx);
 const char* kyd_last_error(const kyd_ctx* ctx); /* ctx may be NULL: last creation error */
 

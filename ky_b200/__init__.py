@@ -91,7 +91,7 @@ class EntryParams(C.Structure):
     _fields_ = [("sub_width", C.c_int), ("sub_height", C.c_int), ("spp", C.c_int), ("depth", C.c_int)]
 
 
-KYD_SYMBOLS = ["kyd_create", "kyd_destroy", "kyd_last_error", "kyd_upload_scene", "kyd_render",
+KYD_SYMBOLS = ["kyd_create", "kyd_create_multi", "kyd_device_count", "kyd_destroy", "kyd_last_error", "kyd_upload_scene", "kyd_render",
                "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest",
                "kyd_film_body_bytes", "kyd_film_header", "kyd_film_encode", "kyd_film_encode_device", "kyd_render_smallpt_f64"]
 
@@ -119,6 +119,8 @@ def kyd():
             raise RuntimeError(f"{kyd_path()} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
         l = C.CDLL(kyd_path(), mode=C.RTLD_GLOBAL)
         l.kyd_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        l.kyd_create_multi.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]
+        l.kyd_device_count.argtypes = [C.c_void_p]
         l.kyd_destroy.argtypes = [C.c_void_p]
         l.kyd_destroy.restype = None
         l.kyd_last_error.argtypes = [C.c_void_p]
@@ -227,15 +229,24 @@ def host_sampler_floats(seed, x, y, sample_index, n):
 
 
 class Device:
-    """One kyd context (one CUDA device, one stream)."""
+    """One kyd context: one CUDA device and one stream, or -- `device` a list of ordinals -- a multi-GPU context
+    (kyd_create_multi) whose renders split the sample range over the devices and sum the partial films on the first."""
 
     def __init__(self, device=0):
         self._ctx = C.c_void_p()
-        rc = kyd().kyd_create(C.byref(self._ctx), device)
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*device)
+            rc = kyd().kyd_create_multi(C.byref(self._ctx), arr, len(device))
+        else:
+            rc = kyd().kyd_create(C.byref(self._ctx), device)
         if rc != 0:
             msg = kyd().kyd_last_error(None).decode()
             self._ctx = None
             raise RuntimeError(f"kyd_create failed ({rc}): {msg}")
+
+    @property
+    def device_count(self):
+        return kyd().kyd_device_count(self._ctx)
 
     def close(self):
         if self._ctx:

@@ -19,6 +19,8 @@ struct kyd_ctx
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    bool events_recorded = false;   // ev_begin / ev_end hold a render's interval
+    bool counters_in_flight = false; // an asynchronous render's counters have not been folded into stats yet
     std::string error;
 
     bool has_scene = false;
@@ -41,16 +43,36 @@ struct kyd_ctx
     int64_t wave_paths = 0;
     bool stage_timing = false; // KYD_STAGE_TIMING=1: per-stage CUDA-event times in kyd_stats::stage_ms
     StageTimer timer;
+
+    // multi-GPU context (kyd_create_multi): this context is rank 0; the others render the rest of the sample range on
+    // their own devices and their partial films are summed here in rank order (kyd_multi section below)
+    std::vector<kyd_ctx*> peers;
+    std::vector<bool> peer_direct;       // rank r's partial film is read in place (same device, or peer access enabled)
+    std::vector<float*> peer_staging;    // staging buffers on this device for peers without peer access
+    std::vector<size_t> peer_staging_capacity;
+    std::vector<cudaEvent_t> peer_done;  // rank r's partial film is complete
+    cudaEvent_t sum_done = nullptr;      // rank 0 has read the peers' partial films
 };
 
 namespace {
 
 std::string g_create_error;
 
-// c_scene is one symbol per device: remember which context's scene it holds
-std::mutex g_scene_mutex;
-const kyd_ctx* g_scene_owner[2][64] = {};               // [small-scene build, large-scene build of the kernels]
-unsigned long long g_scene_owner_generation[2][64] = {};
+// c_scene is ONE __constant__ symbol per device (and per build of the kernels), shared by every context on that device.
+// A render therefore owns the symbol for its whole launch sequence: `launch` is held while the sequence is enqueued, and
+// a render that has to replace the symbol's contents, or that runs on another stream than the previous user, first
+// makes its stream wait for `last_use` (recorded behind the previous user's last kernel).  Two contexts on one GPU
+// driven from two host threads thus take turns per render instead of tracing each other's scene.
+struct SceneSlot
+{
+    std::mutex launch;
+    const kyd_ctx* owner = nullptr;
+    unsigned long long generation = 0;
+    cudaEvent_t last_use = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
+};
+SceneSlot g_scene_slot[2][64];   // [small-scene build, large-scene build of the kernels][device]
 
 int fail(kyd_ctx* ctx, int code, const std::string& msg)
 {
@@ -154,6 +176,10 @@ int validate(kyd_ctx* ctx, const kyd_render_desc* d)
     if (d->spp <= 0) return fail(ctx, KYD_ERR_INVALID, "spp must be positive");
     if (d->sample_begin < 0 || d->sample_end < d->sample_begin || d->sample_end > (1 << 24))
         return fail(ctx, KYD_ERR_INVALID, "bad sample range");
+    // every sample weighs 1/spp and the job has max(1, spp) of them (ky.cpp:3712-3723); indices beyond would push the
+    // weights' sum above 1 (and the trapezoidal sampler's sub-pixel index out of its 2x2 grid)
+    if (d->sample_end > (d->spp > 1 ? d->spp : 1))
+        return fail(ctx, KYD_ERR_INVALID, "bad sample range: sample_end exceeds spp");
     switch (d->integrator)
     {
     case KYD_INT_POSITION: case KYD_INT_NORMAL: case KYD_INT_BASECOLOR: case KYD_INT_DIRECT_LIGHTING:
@@ -181,22 +207,35 @@ int validate(kyd_ctx* ctx, const kyd_render_desc* d)
     return KYD_OK;
 }
 
-// makes the device's constant scene the one of this context
-int bind_scene(kyd_ctx* ctx, cudaStream_t stream)
+// makes the device's constant scene the one of this context; the caller holds slot.launch
+int bind_scene(kyd_ctx* ctx, SceneSlot& slot, cudaStream_t stream)
 {
-    std::lock_guard<std::mutex> lock(g_scene_mutex);
-    int dev = ctx->device & 63;
-    const int big = ctx->scene.bvh_nodes != nullptr;
-    if (g_scene_owner[big][dev] != ctx || g_scene_owner_generation[big][dev] != ctx->scene_generation)
+    const bool big = ctx->scene.bvh_nodes != nullptr;
+    if (!slot.last_use)
+        KYD_CUDA(ctx, cudaEventCreateWithFlags(&slot.last_use, cudaEventDisableTiming));
+    const bool replace = slot.owner != ctx || slot.generation != ctx->scene_generation;
+    // kernels of the previous user may still read the symbol (replace), or ran on another stream whose order against
+    // this one nothing else establishes (a later owner waits only for the LAST user's event, so users are chained)
+    if (slot.used && (replace || slot.last_stream != stream))
+        KYD_CUDA(ctx, cudaStreamWaitEvent(stream, slot.last_use, 0));
+    if (replace)
     {
-        KYD_CUDA(ctx, cudaDeviceSynchronize()); // another context's kernels may still read c_scene
         if (big) kyd_big::upload_scene_constant(ctx->scene, stream);
         else upload_scene_constant(ctx->scene, stream);
         KYD_CUDA(ctx, cudaGetLastError());
-        g_scene_owner[big][dev] = ctx;
-        g_scene_owner_generation[big][dev] = ctx->scene_generation;
+        slot.owner = ctx;
+        slot.generation = ctx->scene_generation;
     }
     return KYD_OK;
+}
+
+// bytes of wavefront state per path slot under `plan` (ensure_wave_buffers, kyd_kernels.cu)
+size_t wave_bytes_per_path(const WavefrontPlan& plan, int n_lights)
+{
+    size_t b = 64 + 8 * 4;                                   // path record, 2 ray queues + 4 lobe queues + 2 vertex queues
+    if (plan.nee) b += (size_t)n_lights * (128 + 2 * 4);      // light-sampling lines + pair queues
+    if (plan.split) b += 96;                                  // vertex records
+    return b;
 }
 
 int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cudaStream_t stream, bool timed)
@@ -208,28 +247,58 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
     rp.lighting = d->lighting; rp.sampler = d->sampler; rp.seed = d->seed; rp.flags = d->flags;
     rp.weight = (float)(1. / d->spp);
 
-    int rc = bind_scene(ctx, stream);
-    if (rc != KYD_OK) return rc;
-
-    KYD_CUDA(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(DevCounters), stream));
-    if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_begin, stream));
-
-    uint64_t launches = 0;
     const bool wavefront = !(d->flags & KYD_FLAG_FUSED) &&
         (d->integrator == KYD_INT_PT_ITERATION || d->integrator == KYD_INT_DIRECT_LIGHTING);
+    int64_t capacity = 0;
     if (wavefront)
     {
         // wave size: the caller's choice, else 16 Mi paths (or the whole job if it is smaller).  Measured on
         // B200 (profiles/r01_wave_sweep.txt): throughput grows with the wave up to the whole 4K film --
         // launch gaps and wave tails cost more than L2 residency of the path state would win.
         const int64_t job = (int64_t)d->width * d->height * (int64_t)(d->sample_end - d->sample_begin);
-        int64_t capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 24;
+        capacity = ctx->wave_paths > 0 ? ctx->wave_paths : (int64_t)1 << 24;
         if (capacity > ((int64_t)1 << 24)) capacity = (int64_t)1 << 24;   // pair-queue entries carry the slot in 24 bits
         if (capacity > job) capacity = job;
         if (capacity < 1024) capacity = 1024;
         // light-sampling lines (128 B per light and path) and vertex records (96 B per path) only where the plan uses them
         const WavefrontPlan plan = wavefront_plan(rp, ctx->scene);
-        KYD_CUDA(ctx, (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, plan.nee ? ctx->scene.n_lights : 0, plan.split));
+        const int nee_lights = plan.nee ? ctx->scene.n_lights : 0;
+        // Results do not depend on the wave size, so memory decides it where it is short (a GPU shared with other work,
+        // many lights: 136 B per light and path): the default is capped by what is free now, and an allocation that
+        // still fails is retried with half the wave down to 64 Ki paths.
+        if (ctx->wave.capacity < capacity || ctx->wave.max_lights < nee_lights || (plan.split && !ctx->wave.has_vertex))
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+            {
+                const size_t held = (size_t)ctx->wave.capacity * wave_bytes_per_path(plan, ctx->wave.max_lights);
+                const int64_t fit = (int64_t)((free_b + held) / 10 * 9 / wave_bytes_per_path(plan, nee_lights > ctx->wave.max_lights ? nee_lights : ctx->wave.max_lights));
+                if (capacity > fit && ctx->wave_paths == 0) capacity = fit < 65536 ? 65536 : fit;
+            }
+            for (;;)
+            {
+                const cudaError_t e = (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, nee_lights, plan.split);
+                if (e == cudaSuccess) break;
+                cudaGetLastError();   // clear the sticky-free allocation error
+                if (e != cudaErrorMemoryAllocation || capacity <= 65536)
+                    return fail(ctx, KYD_ERR_CUDA, std::string("wavefront buffers: ") + cudaGetErrorString(e));
+                capacity /= 2;
+            }
+            if (capacity > ctx->wave.capacity) capacity = ctx->wave.capacity;
+        }
+    }
+
+    SceneSlot& slot = g_scene_slot[ctx->scene.bvh_nodes != nullptr][ctx->device & 63];
+    std::lock_guard<std::mutex> lock(slot.launch);   // the symbol is ours until the launch sequence is enqueued
+    int rc = bind_scene(ctx, slot, stream);
+    if (rc != KYD_OK) return rc;
+
+    KYD_CUDA(ctx, cudaMemsetAsync(ctx->counters_dev, 0, sizeof(DevCounters), stream));
+    if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_begin, stream));
+
+    uint64_t launches = 0;
+    if (wavefront)
+    {
         ctx->timer.stream = stream;
         if (ctx->scene.bvh_nodes)
             kyd_big::launch_render_wavefront(rp, ctx->scene, ctx->wave, capacity, film_dev, ctx->counters_dev, stream, ctx->sm_count, &launches,
@@ -246,27 +315,41 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
     }
     KYD_CUDA(ctx, cudaGetLastError());
 
-    if (timed) KYD_CUDA(ctx, cudaEventRecord(ctx->ev_end, stream));
+    if (timed)
+    {
+        KYD_CUDA(ctx, cudaEventRecord(ctx->ev_end, stream));
+        ctx->events_recorded = true;
+    }
     KYD_CUDA(ctx, cudaMemcpyAsync(ctx->counters_pinned, ctx->counters_dev, sizeof(DevCounters), cudaMemcpyDeviceToHost, stream));
+    KYD_CUDA(ctx, cudaEventRecord(slot.last_use, stream));
+    slot.last_stream = stream;
+    slot.used = true;
 
     ctx->stats = kyd_stats{};
     ctx->stats.samples = (uint64_t)d->width * d->height * (uint64_t)(d->sample_end - d->sample_begin);
     ctx->stats.kernel_launches = launches;
+    ctx->counters_in_flight = true;
     return KYD_OK;
 }
 
-void finish_stats(kyd_ctx* ctx, bool timed)
+// folds the counters of the last render into ctx->stats (the caller has synchronised with its stream)
+void finish_stats(kyd_ctx* ctx)
 {
+    if (!ctx->counters_in_flight)
+        return;
+    ctx->counters_in_flight = false;
     ctx->stats.rays = ctx->counters_pinned->rays;
     ctx->stats.rays_traced = ctx->counters_pinned->rays_traced;
     ctx->stats.shade_vertices = ctx->counters_pinned->shade_vertices;
     ctx->stats.shade_light_lines = ctx->counters_pinned->shade_lines;
     if (ctx->stage_timing) ctx->timer.collect(ctx->stats.stage_ms);
-    if (timed)
+    if (ctx->events_recorded)
     {
         float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end);
-        ctx->stats.device_ms = ms;
+        if (cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end) == cudaSuccess)
+            ctx->stats.device_ms = ms;
+        else
+            cudaGetLastError();   // an interval that is not complete is not an error of the next call
     }
 }
 
@@ -290,7 +373,9 @@ int kyd_create(kyd_ctx** out_ctx, int device)
     auto cleanup = [&](const std::string& msg) { g_create_error = msg; kyd_destroy(ctx); return KYD_ERR_CUDA; };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
+    // a BLOCKING stream: ordered against the device's legacy default stream, so work a caller queued there (torch's
+    // default stream: film.zero_(), an earlier reduce) is complete before a render touches the film, and vice versa
+    if ((e = cudaStreamCreate(&ctx->stream)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&ctx->ev_begin)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaEventCreate(&ctx->ev_end)) != cudaSuccess) return cleanup(cudaGetErrorString(e));
     if ((e = cudaMalloc(&ctx->counters_dev, sizeof(DevCounters))) != cudaSuccess) return cleanup(cudaGetErrorString(e));
@@ -304,12 +389,17 @@ int kyd_create(kyd_ctx** out_ctx, int device)
 void kyd_destroy(kyd_ctx* ctx)
 {
     if (!ctx) return;
+    for (kyd_ctx* peer : ctx->peers) kyd_destroy(peer);
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();   // an asynchronous render on a caller's stream may still use the buffers freed below
+    for (float* p : ctx->peer_staging) if (p) cudaFree(p);
+    for (cudaEvent_t e : ctx->peer_done) if (e) cudaEventDestroy(e);
+    if (ctx->sum_done) cudaEventDestroy(ctx->sum_done);
+    for (int b = 0; b < 2; ++b)
     {
-        std::lock_guard<std::mutex> lock(g_scene_mutex);
-        for (int b = 0; b < 2; ++b)
-            if (g_scene_owner[b][ctx->device & 63] == ctx) g_scene_owner[b][ctx->device & 63] = nullptr;
+        SceneSlot& slot = g_scene_slot[b][ctx->device & 63];
+        std::lock_guard<std::mutex> lock(slot.launch);
+        if (slot.owner == ctx) slot.owner = nullptr;
     }
     free_wave_buffers(ctx->wave);
     if (ctx->film_dev) cudaFree(ctx->film_dev);
@@ -363,6 +453,7 @@ struct BvhBuilder
     const std::vector<Box>& boxes;
     std::vector<BvhNode> nodes;
     std::vector<int> prims;
+    int max_depth = 0;   // deepest node (root = 0): the traversal stack holds at most max_depth + 1 entries
 
     explicit BvhBuilder(const std::vector<Box>& b) : boxes(b)
     {
@@ -370,11 +461,12 @@ struct BvhBuilder
         for (size_t i = 0; i < b.size(); ++i) prims[i] = (int)i;
         nodes.reserve(2 * b.size());
         nodes.push_back(BvhNode{});
-        build(0, 0, (int)b.size());
+        build(0, 0, (int)b.size(), 0);
     }
 
-    void build(int node, int first, int count)
+    void build(int node, int first, int count, int depth)
     {
+        if (depth > max_depth) max_depth = depth;
         Box bound{ { 3.4e38f, 3.4e38f, 3.4e38f }, { -3.4e38f, -3.4e38f, -3.4e38f } };
         float clo[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, chi[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
         for (int k = first; k < first + count; ++k)
@@ -409,8 +501,8 @@ struct BvhBuilder
         nodes.push_back(BvhNode{});
         nodes[node].left = left;
         nodes[node].count = 0;
-        build(left, first, mid - first);
-        build(left + 1, mid, first + count - mid);
+        build(left, first, mid - first, depth + 1);
+        build(left + 1, mid, first + count - mid, depth + 1);
     }
 };
 
@@ -430,6 +522,11 @@ int upload_big_scene(kyd_ctx* ctx, const kyd_scene_desc* sc, DevScene& d)
         boxes[i] = shape_box(shapes[i]);
     }
     BvhBuilder bvh(boxes);
+    // bvh_query (kyd_device.cuh) walks with a fixed stack of KYD_BVH_STACK = 48 entries: popping a node at depth k
+    // leaves at most k siblings below it, so depth + 2 entries suffice.  The median split halves the count per level
+    // (4000 surfaces: depth 10); anything deeper is refused here rather than silently skipped there.
+    if (bvh.max_depth + 2 > 48)
+        return fail(ctx, KYD_ERR_LIMIT, "bounding-volume hierarchy deeper than the traversal stack");
     auto align = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_shapes = 0, o_mat = align(o_shapes + sizeof(DevShape) * n), o_light = align(o_mat + sizeof(int) * n),
                  o_nodes = align(o_light + sizeof(int) * n), o_prims = align(o_nodes + sizeof(BvhNode) * bvh.nodes.size()),
@@ -441,11 +538,13 @@ int upload_big_scene(kyd_ctx* ctx, const kyd_scene_desc* sc, DevScene& d)
     memcpy(host.data() + o_nodes, bvh.nodes.data(), sizeof(BvhNode) * bvh.nodes.size());
     memcpy(host.data() + o_prims, bvh.prims.data(), sizeof(int) * n);
     KYD_CUDA(ctx, cudaSetDevice(ctx->device));
-    KYD_CUDA(ctx, cudaDeviceSynchronize());   // kernels of an earlier render may still read the previous scene
+    void* fresh = nullptr;
+    KYD_CUDA(ctx, cudaMalloc(&fresh, total));
+    cudaError_t e = cudaMemcpy(fresh, host.data(), total, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // kernels of an earlier render may still read the previous scene
+    if (e != cudaSuccess) { cudaFree(fresh); KYD_CUDA(ctx, e); }
     if (ctx->big_scene_dev) cudaFree(ctx->big_scene_dev);
-    ctx->big_scene_dev = nullptr;
-    KYD_CUDA(ctx, cudaMalloc(&ctx->big_scene_dev, total));
-    KYD_CUDA(ctx, cudaMemcpy(ctx->big_scene_dev, host.data(), total, cudaMemcpyHostToDevice));
+    ctx->big_scene_dev = fresh;
     const char* base = (const char*)ctx->big_scene_dev;
     d.big_shape = (const DevShape*)(base + o_shapes);
     d.big_material = (const int*)(base + o_mat);
@@ -462,7 +561,10 @@ int upload_big_scene(kyd_ctx* ctx, const kyd_scene_desc* sc, DevScene& d)
 
 } // namespace
 
-int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
+namespace {
+// builds the device form of the scene into a local copy and commits it to the context only when everything validated: a
+// failed upload leaves the previous scene (host plan AND device symbol) in force
+int upload_scene_one(kyd_ctx* ctx, const kyd_scene_desc* sc)
 {
     if (!ctx) return KYD_ERR_INVALID;
     if (!sc) return fail(ctx, KYD_ERR_INVALID, "scene desc is null");
@@ -471,7 +573,8 @@ int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
         return fail(ctx, KYD_ERR_LIMIT, "scene exceeds KYD_MAX_* limits");
     const bool big = sc->surface_count > KYD_MAX_SURFACES;   // global memory + bounding-volume hierarchy instead of constant memory
 
-    DevScene& d = ctx->scene;
+    std::vector<DevScene> storage(1);
+    DevScene& d = storage[0];
     memset(&d, 0, sizeof(d));
     d.camera.position = f3(sc->camera.position);
     d.camera.front = f3(sc->camera.front);
@@ -499,12 +602,7 @@ int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
         d.surf_material[i] = s.material;
         d.surf_light[i] = s.area_light;
     }
-    if (big)
-    {
-        int rc = upload_big_scene(ctx, sc, d);
-        if (rc != KYD_OK) return rc;
-    }
-    else
+    if (!big)
     {
         // traversal copy grouped by kind; list order inside a group (ties are resolved by surface index, see scene_closest)
         const int group_kind[4] = { KYD_SHAPE_RECTANGLE, KYD_SHAPE_SPHERE, KYD_SHAPE_TRIANGLE, KYD_SHAPE_DISK };
@@ -566,10 +664,222 @@ int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
         if (!(sphere_area && sc->light_count > 1))
             d.light_surface[l] = -2;
     }
+    if (big)
+    {
+        // last step that can fail; it replaces the device allocation only once the new one is filled
+        int rc = upload_big_scene(ctx, sc, d);
+        if (rc != KYD_OK) return rc;
+        for (int l = 0; l < KYD_MAX_LIGHTS; ++l)
+        {
+            const bool sphere_area = l < sc->light_count && sc->lights[l].kind == KYD_LIGHT_AREA && d.light_shape[l].kind == KYD_SHAPE_SPHERE;
+            if (!(sphere_area && sc->light_count > 1))
+                d.light_surface[l] = -2;
+        }
+    }
+    else if (ctx->big_scene_dev)
+    {
+        // back to a constant-memory scene: the large scene's allocation is no longer needed
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        cudaFree(ctx->big_scene_dev);
+        ctx->big_scene_dev = nullptr;
+    }
+    ctx->scene = d;
     ctx->has_scene = true;
     ctx->scene_generation++;
     return KYD_OK;
 }
+} // namespace
+
+int kyd_upload_scene(kyd_ctx* ctx, const kyd_scene_desc* sc)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    int rc = upload_scene_one(ctx, sc);
+    for (kyd_ctx* peer : ctx->peers)
+    {
+        if (rc != KYD_OK) break;
+        rc = upload_scene_one(peer, sc);
+        if (rc != KYD_OK) ctx->error = peer->error;
+    }
+    return rc;
+}
+
+namespace {
+
+// ---- multi-GPU context (kyd_create_multi) ------------------------------------------------------------------------
+// The path shards by SAMPLE INDEX: rank r of n renders a contiguous share of [sample_begin, sample_end)
+// for every pixel into an unclamped partial film on its own GPU (each sample already weighs 1/spp), rank 0 then adds
+// the partials to its own in rank order -- one kernel on rank 0's GPU that loads the peers' films through their NVLink
+// peer mappings (or from a staging copy where peer access is not available) -- and clamps after the sum, because the
+// reference clamps after the spp-sum (ky.cpp:3721-3726).  One host thread per GPU enqueues its rank's launches.
+void sample_share(int begin, int end, int n, int r, int* b, int* e)
+{
+    const int total = end - begin, base = total / n, extra = total % n;
+    *b = begin + r * base + (r < extra ? r : extra);
+    *e = *b + base + (r < extra ? 1 : 0);
+}
+
+int multi_render(kyd_ctx* ctx, const kyd_render_desc* d, float* film_root, cudaStream_t stream)
+{
+    const int n = 1 + (int)ctx->peers.size();
+    const size_t floats = (size_t)d->width * d->height * 3;
+    std::vector<kyd_render_desc> share(n, *d);
+    for (int r = 0; r < n; ++r)
+    {
+        sample_share(d->sample_begin, d->sample_end, n, r, &share[r].sample_begin, &share[r].sample_end);
+        share[r].flags = d->flags & ~(uint32_t)KYD_FLAG_CLAMP;
+        if (r > 0) share[r].flags &= ~(uint32_t)KYD_FLAG_ACCUMULATE;
+    }
+    std::vector<int> rcs(n, KYD_OK);
+    std::vector<std::thread> pool;
+    for (int r = 1; r < n; ++r)
+    {
+        if (share[r].sample_end == share[r].sample_begin) continue;   // nothing to add
+        pool.emplace_back([&, r] {
+            kyd_ctx* peer = ctx->peers[r - 1];
+            cudaError_t e = cudaSetDevice(peer->device);
+            if (e != cudaSuccess) { rcs[r] = fail(peer, KYD_ERR_CUDA, cudaGetErrorString(e)); return; }
+            if ((rcs[r] = ensure_film(peer, floats)) != KYD_OK) return;
+            if ((rcs[r] = render_to_device(peer, &share[r], peer->film_dev, peer->stream, true)) != KYD_OK) return;
+            e = cudaEventRecord(ctx->peer_done[r - 1], peer->stream);
+            if (e != cudaSuccess) rcs[r] = fail(peer, KYD_ERR_CUDA, cudaGetErrorString(e));
+        });
+    }
+    rcs[0] = render_to_device(ctx, &share[0], film_root, stream, true);
+    for (auto& t : pool) t.join();
+    cudaSetDevice(ctx->device);
+    for (int r = 0; r < n; ++r)
+        if (rcs[r] != KYD_OK)
+        {
+            if (r > 0) ctx->error = "rank " + std::to_string(r) + ": " + ctx->peers[r - 1]->error;
+            return rcs[r];
+        }
+    // the sum: rank order, peers' films read in place over their peer mappings
+    const float* parts[KYD_MAX_MULTI] = {};
+    int n_parts = 0;
+    for (int r = 1; r < n; ++r)
+    {
+        if (share[r].sample_end == share[r].sample_begin) continue;
+        kyd_ctx* peer = ctx->peers[r - 1];
+        KYD_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->peer_done[r - 1], 0));
+        const float* view = peer->film_dev;
+        if (!ctx->peer_direct[r - 1])
+        {
+            if (ctx->peer_staging_capacity[r - 1] < floats)
+            {
+                if (ctx->peer_staging[r - 1]) cudaFree(ctx->peer_staging[r - 1]);
+                ctx->peer_staging[r - 1] = nullptr;
+                ctx->peer_staging_capacity[r - 1] = 0;
+                KYD_CUDA(ctx, cudaMalloc(&ctx->peer_staging[r - 1], floats * sizeof(float)));
+                ctx->peer_staging_capacity[r - 1] = floats;
+            }
+            KYD_CUDA(ctx, cudaMemcpyPeerAsync(ctx->peer_staging[r - 1], ctx->device, peer->film_dev, peer->device, floats * sizeof(float), stream));
+            view = ctx->peer_staging[r - 1];
+        }
+        parts[n_parts++] = view;
+    }
+    launch_sum_partials(film_root, parts, n_parts, (int64_t)floats, (d->flags & KYD_FLAG_CLAMP) != 0, ctx->sm_count, stream);
+    KYD_CUDA(ctx, cudaGetLastError());
+    KYD_CUDA(ctx, cudaEventRecord(ctx->ev_end, stream));   // the job's interval on rank 0 ends behind the sum
+    // the peers' film buffers are read by rank 0's stream: their next render must not overwrite them earlier
+    KYD_CUDA(ctx, cudaEventRecord(ctx->sum_done, stream));
+    for (kyd_ctx* peer : ctx->peers)
+    {
+        cudaSetDevice(peer->device);
+        cudaStreamWaitEvent(peer->stream, ctx->sum_done, 0);
+    }
+    cudaSetDevice(ctx->device);
+    ctx->stats.kernel_launches += 1;
+    return KYD_OK;
+}
+
+int render_any(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cudaStream_t stream)
+{
+    if (!ctx->peers.empty())
+        return multi_render(ctx, d, film_dev, stream);
+    return render_to_device(ctx, d, film_dev, stream, true);
+}
+
+// folds the ranks' counters into rank 0's stats: sums, and the longest device interval
+void finish_stats_all(kyd_ctx* ctx)
+{
+    const bool fresh = ctx->counters_in_flight;
+    finish_stats(ctx);
+    if (!fresh) return;
+    for (kyd_ctx* peer : ctx->peers)
+    {
+        if (!peer->counters_in_flight) continue;
+        cudaSetDevice(peer->device);
+        cudaStreamSynchronize(peer->stream);
+        finish_stats(peer);
+        const kyd_stats& p = peer->stats;
+        ctx->stats.rays += p.rays;
+        ctx->stats.rays_traced += p.rays_traced;
+        ctx->stats.kernel_launches += p.kernel_launches;
+        ctx->stats.samples += p.samples;
+        ctx->stats.shade_vertices += p.shade_vertices;
+        ctx->stats.shade_light_lines += p.shade_light_lines;
+        for (int k = 0; k < 8; ++k)
+            if (p.stage_ms[k] > ctx->stats.stage_ms[k]) ctx->stats.stage_ms[k] = p.stage_ms[k];
+    }
+    cudaSetDevice(ctx->device);
+}
+
+} // namespace
+
+int kyd_create_multi(kyd_ctx** out_ctx, const int* devices, int n)
+{
+    if (!out_ctx) return fail(nullptr, KYD_ERR_INVALID, "out_ctx is null");
+    *out_ctx = nullptr;
+    if (!devices || n < 1 || n > KYD_MAX_MULTI) return fail(nullptr, KYD_ERR_INVALID, "device list must hold 1..KYD_MAX_MULTI ordinals");
+    kyd_ctx* root = nullptr;
+    int rc = kyd_create(&root, devices[0]);
+    if (rc != KYD_OK) return rc;
+    for (int r = 1; r < n; ++r)
+    {
+        kyd_ctx* peer = nullptr;
+        rc = kyd_create(&peer, devices[r]);
+        if (rc != KYD_OK) { kyd_destroy(root); return rc; }
+        root->peers.push_back(peer);
+        root->peer_staging.push_back(nullptr);
+        root->peer_staging_capacity.push_back(0);
+        // the partial film of a peer on another GPU is read in place when the GPUs are peers (NVLink / NVSwitch on a B200 box)
+        bool direct = devices[r] == devices[0];
+        if (!direct)
+        {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devices[0], devices[r]);
+            if (can)
+            {
+                cudaSetDevice(devices[0]);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+                direct = e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled;
+                cudaGetLastError();
+            }
+        }
+        root->peer_direct.push_back(direct);
+        cudaEvent_t ev = nullptr;
+        cudaSetDevice(devices[r]);
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess)
+        {
+            g_create_error = "cudaEventCreate failed";
+            kyd_destroy(root);
+            return KYD_ERR_CUDA;
+        }
+        root->peer_done.push_back(ev);
+    }
+    cudaSetDevice(devices[0]);
+    if (n > 1 && cudaEventCreateWithFlags(&root->sum_done, cudaEventDisableTiming) != cudaSuccess)
+    {
+        g_create_error = "cudaEventCreate failed";
+        kyd_destroy(root);
+        return KYD_ERR_CUDA;
+    }
+    *out_ctx = root;
+    return KYD_OK;
+}
+
+int kyd_device_count(const kyd_ctx* ctx) { return ctx ? 1 + (int)ctx->peers.size() : 0; }
 
 int kyd_render(kyd_ctx* ctx, const kyd_render_desc* d, float* film_rgb)
 {
@@ -585,9 +895,9 @@ int kyd_render(kyd_ctx* ctx, const kyd_render_desc* d, float* film_rgb)
     if ((rc = ensure_film(ctx, floats)) != KYD_OK) return rc;
     if ((rc = ensure_pinned(ctx, floats)) != KYD_OK) return rc;
 
-    if ((rc = render_to_device(ctx, d, ctx->film_dev, ctx->stream, true)) != KYD_OK) return rc;
+    if ((rc = render_any(ctx, d, ctx->film_dev, ctx->stream)) != KYD_OK) return rc;
     if ((rc = download_film(ctx, ctx->film_dev, ctx->film_pinned, film_rgb, floats * sizeof(float))) != KYD_OK) return rc;
-    finish_stats(ctx, true);
+    finish_stats_all(ctx);
     return KYD_OK;
 }
 
@@ -600,11 +910,11 @@ int kyd_render_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_rgb_de
     if (rc != KYD_OK) return rc;
     KYD_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream;
-    if ((rc = render_to_device(ctx, d, film_rgb_device, stream, true)) != KYD_OK) return rc;
+    if ((rc = render_any(ctx, d, film_rgb_device, stream)) != KYD_OK) return rc;
     if (!cuda_stream)
     {
         KYD_CUDA(ctx, cudaStreamSynchronize(stream));
-        finish_stats(ctx, true);
+        finish_stats_all(ctx);
     }
     return KYD_OK;
 }
@@ -702,7 +1012,7 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out)
     // an asynchronous kyd_render_device leaves the counters in flight: settle them
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    finish_stats(ctx, true);
+    finish_stats_all(ctx);
     *out = ctx->stats;
     return KYD_OK;
 }
@@ -757,6 +1067,7 @@ int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths)
     if (!ctx) return KYD_ERR_INVALID;
     if (paths < 0) return fail(ctx, KYD_ERR_INVALID, "wave size must be >= 0");
     ctx->wave_paths = paths;
+    for (kyd_ctx* peer : ctx->peers) peer->wave_paths = paths;
     return KYD_OK;
 }
 

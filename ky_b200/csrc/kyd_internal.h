@@ -59,6 +59,10 @@ void launch_render_pixels(const RenderParams& rp, float* film_dev, DevCounters* 
 
 void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 
+// film[i] = clamp?(((film[i] + parts[0][i]) + parts[1][i]) + ...): the end of a multi-GPU job on rank 0's device; the
+// parts are the other ranks' partial films, addressable from this device (peer mappings or staging copies)
+void launch_sum_partials(float* film_dev, const float* const* parts, int n_parts, int64_t n, bool clamp, int sm_count, cudaStream_t stream);
+
 void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 

@@ -385,6 +385,54 @@ void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream)
     k_clamp<<<(unsigned)((n + block - 1) / block), block, 0, stream>>>(film_dev, n);
 }
 
+// ---- multi-GPU: the partial films of the other ranks added in rank order, clamp after the sum (ky.cpp:3721-3726) ----
+// One pass over rank 0's film; the peers' films are loaded in place through their peer mappings (16-byte loads: the
+// NVLink transfer IS the kernel's load stream, nothing is staged), so the reduce and the clamp cost one kernel.
+struct PartTable { const float* p[KYD_MAX_MULTI]; };
+
+__global__ void __launch_bounds__(256) k_sum_partials(float* __restrict__ film, PartTable parts, int n_parts, int64_t n, int64_t n4, int clamp)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;   // n4: float4 units handled by the vector loop (0 for unaligned films)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride)
+    {
+        float4 v = reinterpret_cast<float4*>(film)[i];
+        for (int r = 0; r < n_parts; ++r)
+        {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(parts.p[r]) + i);
+            v.x = v.x + a.x; v.y = v.y + a.y; v.z = v.z + a.z; v.w = v.w + a.w;
+        }
+        if (clamp)
+        {
+            v.x = clamp_std(v.x, 0.f, 1.f); v.y = clamp_std(v.y, 0.f, 1.f); v.z = clamp_std(v.z, 0.f, 1.f); v.w = clamp_std(v.w, 0.f, 1.f);
+        }
+        reinterpret_cast<float4*>(film)[i] = make_float4(film_value(v.x), film_value(v.y), film_value(v.z), film_value(v.w));
+    }
+    for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        float v = film[i];
+        for (int r = 0; r < n_parts; ++r)
+            v = v + parts.p[r][i];
+        if (clamp)
+            v = clamp_std(v, 0.f, 1.f);
+        film[i] = film_value(v);
+    }
+}
+
+void launch_sum_partials(float* film_dev, const float* const* parts, int n_parts, int64_t n, bool clamp, int sm_count, cudaStream_t stream)
+{
+    if (n_parts == 0 && !clamp)
+        return;
+    PartTable t{};
+    bool aligned = ((uintptr_t)film_dev & 15u) == 0;
+    for (int r = 0; r < n_parts; ++r)
+    {
+        t.p[r] = parts[r];
+        aligned = aligned && ((uintptr_t)parts[r] & 15u) == 0;
+    }
+    // (cudaMalloc'ed films are 256-byte aligned; a caller's odd pointer falls back to the scalar loop)
+    k_sum_partials<<<sm_count * 8, 256, 0, stream>>>(film_dev, t, n_parts, n, aligned ? n >> 2 : 0, clamp ? 1 : 0);
+}
+
 // ---- self-tests of the exactness-critical fast paths ---------------------------------------------------
 // out[0] = bit patterns whose fast result differs from the definition, out[1] = patterns that took the slow path
 __global__ void k_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* __restrict__ out)
