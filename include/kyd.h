@@ -193,6 +193,7 @@ typedef struct kyd_stats
                                    filled when the context was created with KYD_STAGE_TIMING=1 in the environment */
     uint64_t shade_vertices;      /* wavefront: path vertices shaded */
     uint64_t shade_light_lines;   /* wavefront: light-sampling lines written by shade (64 B, 96 B with a live BSDF query) */
+    uint64_t intersect_rays;      /* wavefront: closest-hit queries traversed by the intersect stage (part of rays_traced) */
 } kyd_stats;
 
 typedef struct kyd_ctx kyd_ctx;
@@ -238,8 +239,12 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out);
    the `count` float bit patterns starting at `first`; out2[0] = mismatches, out2[1] = inputs that took the slow path.
    KYD_SELFTEST_POW: compares powf's fast path (exp2(y log2 x) + rounding-interval check) with its definition
    (float)pow((double)x, (double)y) on `count` argument pairs derived from the indices first.. (Phong's exponents
-   30 / 90 / 5000 and their 1/(n+1), random exponents; bases dense next to 1; negative bases with integer exponents) */
-enum kyd_selftest_kind { KYD_SELFTEST_RSQRT = 0, KYD_SELFTEST_POW = 1 };
+   30 / 90 / 5000 and their 1/(n+1), random exponents; bases dense next to 1; negative bases with integer exponents)
+   KYD_SELFTEST_TRAVERSAL: compares the two-phase traversal of the wavefront kernels (conservative classification of a ray
+   against each rectangle, the reference's own tests only for candidates; kyd_device.cuh) with the reference's list walk
+   (ky.cpp:3172-3206) on `count` adversarial rays through the UPLOADED scene (at most KYD_MAX_SURFACES surfaces) -- closest
+   hit, occlusion and occlusion-before-a-surface queries; out2[0] = queries that disagree, out2[1] = rays that hit a surface. */
+enum kyd_selftest_kind { KYD_SELFTEST_RSQRT = 0, KYD_SELFTEST_POW = 1, KYD_SELFTEST_TRAVERSAL = 2 };
 int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2);
 
 /* size in paths of one wavefront (0 = library default, 2^24; larger values are clamped to 2^24); tuning knob, results do

@@ -84,7 +84,7 @@ class RenderDesc(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", C.c_uint64), ("rays", C.c_uint64), ("rays_traced", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("stage_ms", C.c_double * 8),
-                ("shade_vertices", C.c_uint64), ("shade_light_lines", C.c_uint64)]
+                ("shade_vertices", C.c_uint64), ("shade_light_lines", C.c_uint64), ("intersect_rays", C.c_uint64)]
 
 
 class EntryParams(C.Structure):

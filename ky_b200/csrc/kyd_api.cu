@@ -144,6 +144,122 @@ DevShape convert_shape(const kyd_shape& s)
     return d;
 }
 
+// The rectangle as the parallelogram p1 + u (p0 - p1) + v (p2 - p1), in double (kyd_device.cuh: rect_classify)
+RectCull make_rect_cull(const DevShape& s)
+{
+    RectCull c{};
+    const double b[3] = { s.p1.x, s.p1.y, s.p1.z };
+    const double eu[3] = { s.p0.x - b[0], s.p0.y - b[1], s.p0.z - b[2] };
+    const double ev[3] = { s.p2.x - b[0], s.p2.y - b[1], s.p2.z - b[2] };
+    const double p3[3] = { s.p3.x, s.p3.y, s.p3.z };
+    double n[3] = { eu[1] * ev[2] - eu[2] * ev[1], eu[2] * ev[0] - eu[0] * ev[2], eu[0] * ev[1] - eu[1] * ev[0] };
+    const double area = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    double d1 = 0, d2 = 0, dev = 0;
+    for (int a = 0; a < 3; ++a)
+    {
+        d1 += (eu[a] - ev[a]) * (eu[a] - ev[a]);              // |p0 - p2|^2
+        d2 += (eu[a] + ev[a]) * (eu[a] + ev[a]);              // |p3 - p1|^2 of the ideal parallelogram
+        const double ideal = b[a] + eu[a] + ev[a];
+        dev += (p3[a] - ideal) * (p3[a] - ideal);
+    }
+    const double diag = std::sqrt(d1 > d2 ? d1 : d2);
+    c.b = make_float3((float)b[0], (float)b[1], (float)b[2]);
+    const bool degenerate = !(area > 1e-30) || !(area < 1e15) || !(diag < 1e15) || !(std::sqrt(dev) <= 0x1p-20 * diag);
+    if (degenerate)
+        return c;   // n = 0: every ray is a candidate
+    for (int a = 0; a < 3; ++a) n[a] /= area;
+    // dual basis in the plane: gu = (ev x n) / (eu . (ev x n)), gv = (n x eu) / (ev . (n x eu))
+    double evxn[3] = { ev[1] * n[2] - ev[2] * n[1], ev[2] * n[0] - ev[0] * n[2], ev[0] * n[1] - ev[1] * n[0] };
+    double nxeu[3] = { n[1] * eu[2] - n[2] * eu[1], n[2] * eu[0] - n[0] * eu[2], n[0] * eu[1] - n[1] * eu[0] };
+    const double su = eu[0] * evxn[0] + eu[1] * evxn[1] + eu[2] * evxn[2];
+    const double sv = ev[0] * nxeu[0] + ev[1] * nxeu[1] + ev[2] * nxeu[2];
+    c.n = make_float3((float)n[0], (float)n[1], (float)n[2]);
+    c.gu = make_float3((float)(evxn[0] / su), (float)(evxn[1] / su), (float)(evxn[2] / su));
+    c.gv = make_float3((float)(nxeu[0] / sv), (float)(nxeu[1] / sv), (float)(nxeu[2] / sv));
+    c.c_area = (float)(0x1p-15 / area);
+    return c;
+}
+
+// axis-aligned rectangle: all four points share one coordinate and the edges p1->p0, p1->p2 each run along one axis;
+// returns the normal axis or -1
+int make_rect_aligned(const DevShape& s, RectAligned* out)
+{
+    const float p[4][3] = { { s.p0.x, s.p0.y, s.p0.z }, { s.p1.x, s.p1.y, s.p1.z }, { s.p2.x, s.p2.y, s.p2.z }, { s.p3.x, s.p3.y, s.p3.z } };
+    for (int a = 0; a < 3; ++a)
+    {
+        if (!(p[0][a] == p[1][a] && p[1][a] == p[2][a] && p[2][a] == p[3][a]))
+            continue;
+        const int b = (a + 1) % 3, c = (a + 2) % 3;
+        // edge p1->p0 along one in-plane axis, p1->p2 along the other, p3 the opposite corner (exactly: same floats)
+        const bool u_b = p[0][c] == p[1][c] && p[2][b] == p[1][b] && p[3][b] == p[0][b] && p[3][c] == p[2][c];
+        const bool u_c = p[0][b] == p[1][b] && p[2][c] == p[1][c] && p[3][c] == p[0][c] && p[3][b] == p[2][b];
+        if (!u_b && !u_c)
+            return -1;
+        double lo_b = p[0][b], hi_b = p[0][b], lo_c = p[0][c], hi_c = p[0][c];
+        for (int k = 1; k < 4; ++k)
+        {
+            lo_b = p[k][b] < lo_b ? p[k][b] : lo_b; hi_b = p[k][b] > hi_b ? p[k][b] : hi_b;
+            lo_c = p[k][c] < lo_c ? p[k][c] : lo_c; hi_c = p[k][c] > hi_c ? p[k][c] : hi_c;
+        }
+        const double area = (hi_b - lo_b) * (hi_c - lo_c);
+        if (!(area > 1e-30) || !(area < 1e15) || !std::isfinite(area))
+            return -1;
+        out->pa = p[0][a];
+        out->lo_b = (float)lo_b;
+        out->lo_c = (float)lo_c;
+        out->gb = (float)(1.0 / (hi_b - lo_b));
+        out->gc = (float)(1.0 / (hi_c - lo_c));
+        out->c_area = (float)(0x1p-15 / area);
+        return a;
+    }
+    return -1;
+}
+
+// classifiers of the first 32 rectangles of the sorted copy, regrouped aligned-x | aligned-y | aligned-z | general
+void build_rect_classifiers(DevScene& d)
+{
+    const int n = d.kind_end[0] < 32 ? d.kind_end[0] : 32;
+    RectAligned aligned[32];
+    int axis[32];
+    for (int k = 0; k < n; ++k)
+        axis[k] = make_rect_aligned(d.sorted_shape[k], &aligned[k]);
+    int pos = 0;
+    for (int a = 0; a < 3; ++a)
+    {
+        for (int k = 0; k < n; ++k)
+            if (axis[k] == a)
+            {
+                d.rect_aligned[pos] = aligned[k];
+                d.rect_order[pos] = k;
+                ++pos;
+            }
+        d.rect_aligned_end[a] = pos;
+    }
+    d.n_rect_general = 0;
+    for (int k = 0; k < n; ++k)
+        if (axis[k] < 0)
+        {
+            d.rect_general[d.n_rect_general++] = make_rect_cull(d.sorted_shape[k]);
+            d.rect_order[pos++] = k;
+        }
+    d.n_rect_cull = pos;
+    // L1 bound of the classified rectangles' vertices around the centre of their bounding box
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (int k = 0; k < n; ++k)
+    {
+        const DevShape& s = d.sorted_shape[k];
+        const float3 pts[4] = { s.p0, s.p1, s.p2, s.p3 };
+        for (const float3& q : pts)
+        {
+            const double v[3] = { q.x, q.y, q.z };
+            for (int a = 0; a < 3; ++a) { lo[a] = v[a] < lo[a] ? v[a] : lo[a]; hi[a] = v[a] > hi[a] ? v[a] : hi[a]; }
+        }
+    }
+    if (n == 0) { for (int a = 0; a < 3; ++a) lo[a] = hi[a] = 0; }
+    d.bound_center = make_float3((float)(0.5 * (lo[0] + hi[0])), (float)(0.5 * (lo[1] + hi[1])), (float)(0.5 * (lo[2] + hi[2])));
+    d.bound_l1 = (float)((0.5 * ((hi[0] - lo[0]) + (hi[1] - lo[1]) + (hi[2] - lo[2]))) * (1.0 + 1e-6) + 1e-30);
+}
+
 int ensure_film(kyd_ctx* ctx, size_t floats)
 {
     if (floats <= ctx->film_capacity)
@@ -342,6 +458,7 @@ void finish_stats(kyd_ctx* ctx)
     ctx->stats.rays_traced = ctx->counters_pinned->rays_traced;
     ctx->stats.shade_vertices = ctx->counters_pinned->shade_vertices;
     ctx->stats.shade_light_lines = ctx->counters_pinned->shade_lines;
+    ctx->stats.intersect_rays = ctx->counters_pinned->intersect_rays;
     if (ctx->stage_timing) ctx->timer.collect(ctx->stats.stage_ms);
     if (ctx->events_recorded)
     {
@@ -623,6 +740,7 @@ int upload_scene_one(kyd_ctx* ctx, const kyd_scene_desc* sc)
         for (int i = 0; i < sc->surface_count; ++i)
             if (d.surf_light[i] >= 0)
                 d.light_surface[d.surf_light[i]] = d.light_surface[d.surf_light[i]] == -1 ? i : -2;
+        build_rect_classifiers(d);   // two-phase traversal (rectangles are group 0 of the sorted copy)
     }
     for (int i = 0; i < sc->material_count; ++i)
     {
@@ -819,6 +937,7 @@ void finish_stats_all(kyd_ctx* ctx)
         ctx->stats.samples += p.samples;
         ctx->stats.shade_vertices += p.shade_vertices;
         ctx->stats.shade_light_lines += p.shade_light_lines;
+        ctx->stats.intersect_rays += p.intersect_rays;
         for (int k = 0; k < 8; ++k)
             if (p.stage_ms[k] > ctx->stats.stage_ms[k]) ctx->stats.stage_ms[k] = p.stage_ms[k];
     }
@@ -1020,12 +1139,26 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out)
 int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2)
 {
     if (!ctx || !out2) return KYD_ERR_INVALID;
-    if (which != KYD_SELFTEST_RSQRT && which != KYD_SELFTEST_POW) return fail(ctx, KYD_ERR_INVALID, "unknown self-test");
+    if (which != KYD_SELFTEST_RSQRT && which != KYD_SELFTEST_POW && which != KYD_SELFTEST_TRAVERSAL)
+        return fail(ctx, KYD_ERR_INVALID, "unknown self-test");
+    if (which == KYD_SELFTEST_TRAVERSAL && (!ctx->has_scene || ctx->scene.bvh_nodes))
+        return fail(ctx, KYD_ERR_NO_SCENE, "the traversal self-test needs an uploaded scene of at most KYD_MAX_SURFACES surfaces");
     KYD_CUDA(ctx, cudaSetDevice(ctx->device));
     unsigned long long* dev = nullptr;
     KYD_CUDA(ctx, cudaMalloc(&dev, 2 * sizeof(unsigned long long)));
     cudaMemsetAsync(dev, 0, 2 * sizeof(unsigned long long), ctx->stream);
-    if (which == KYD_SELFTEST_RSQRT) launch_selftest_rsqrt(first, count, dev, ctx->stream);
+    if (which == KYD_SELFTEST_TRAVERSAL)
+    {
+        SceneSlot& slot = g_scene_slot[0][ctx->device & 63];
+        std::lock_guard<std::mutex> lock(slot.launch);
+        const int rc = bind_scene(ctx, slot, ctx->stream);
+        if (rc != KYD_OK) { cudaFree(dev); return rc; }
+        launch_selftest_traversal(first, count, dev, ctx->stream);
+        cudaEventRecord(slot.last_use, ctx->stream);
+        slot.last_stream = ctx->stream;
+        slot.used = true;
+    }
+    else if (which == KYD_SELFTEST_RSQRT) launch_selftest_rsqrt(first, count, dev, ctx->stream);
     else launch_selftest_pow(first, count, dev, ctx->stream);
     unsigned long long host[2] = { 0, 0 };
     cudaError_t e = cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, ctx->stream);

@@ -1123,6 +1123,323 @@ KYD_DEV bool scene_any_hit_uniform(const Ray& r)
     return hit && r.tmax > KYD_SHAPE_EPSILON;
 }
 
+// ---- two-phase traversal (wavefront kernels, scenes in constant memory) ---------------------------------------------------
+// The reference tests a ray against a rectangle with four edge functions E = ((v_i - o) x (v_j - o)) . d whose signs must
+// agree, then computes t = n.(p0 - o) / n.d and accepts eps < t < tmax (ky.cpp:1261-1297): ~100 instructions, for every
+// rectangle and every ray, although a ray hits about one of them.  Both halves are pure functions, so they may be
+// evaluated in any order and only where they can matter:
+//   phase 1 (warp-uniform loop, ~40 FMA-pipe instructions per rectangle, no division): an approximate hit point in the
+//     rectangle's own (u, v) coordinates CLASSIFIES the ray as certainly outside, certainly inside, or within a band around
+//     the edges; likewise its approximate distance against (eps, tmax);
+//   phase 2 (per lane, over the lane's own candidates read from shared memory): the reference's exact t for candidates, and
+//     the reference's four edge functions only for rays in the band.
+// Why the classification is safe.  With p the exact hit point in the plane, E_ij = (d.n) |v_i - v_j| dist(p, line ij), i.e.
+// (d.n) * Area * min(u, 1-u, v, 1-v) for the nearest edge of the parallelogram.  The float evaluation of E differs from that
+// by at most 8.5 eps M^2 (M = largest |v_i - o|, eps = 2^-24; products, differences and the rounded inputs counted), about
+// 2^-21 M^2.  A ray is called inside (outside) only when every edge function is at least 2^-15 M1^2 in magnitude with the
+// sign of an interior (for one edge: exterior) point, M1 >= M being the L1 bound computed below: 60x the error bound, so
+// the float signs are the exact signs and the reference's test would say the same.  The classifier's own arithmetic
+// (approximate reciprocal, FMA, rounded constants) moves u and v by at most 15 eps M |e| / (Area |d.n|) <= 0.12 of that
+// margin.  The distance test uses tau = 2^-15 M1 / |d.n| + 2^-18 |t| against an error of 2^-20 M / |d.n| + 2^-21 |t|.
+// Anything not certainly outside becomes a candidate, NaNs and infinities included (every comparison with them is false).
+// kyd_selftest(KYD_SELFTEST_TRAVERSAL) compares the three queries with the list walk on adversarial rays (through edges and
+// corners, grazing, starting on surfaces) for the uploaded scene; the film tests compare whole renders with the oracle.
+#ifndef KYD_TWO_PHASE
+#define KYD_TWO_PHASE 1
+#endif
+#define KYD_RECT_SMEM_STRIDE 17   // 15 floats of geometry + surface index, odd stride: lanes on different rectangles hit different banks
+
+#if !KYD_BIG_SCENE
+KYD_DEV float* rect_smem()
+{
+    __shared__ float s[32 * KYD_RECT_SMEM_STRIDE];
+    return s;
+}
+
+// every thread of the block, once, before the first query: exact rectangle data for the per-lane phase, in mask-bit order
+KYD_DEV void stage_rects()
+{
+#if KYD_TWO_PHASE
+    float* s = rect_smem();
+    const int n = c_scene.n_rect_cull;
+    for (int i = threadIdx.x; i < n * 16; i += blockDim.x)
+    {
+        const int k = i >> 4, j = i & 15;
+        const int sorted = c_scene.rect_order[k];
+        const float* shape = reinterpret_cast<const float*>(&c_scene.sorted_shape[sorted]);   // p0, p1, p2, p3, n: 15 floats
+        s[k * KYD_RECT_SMEM_STRIDE + j] = j < 15 ? shape[j] : __int_as_float(c_scene.sorted_surface[sorted]);
+    }
+    __syncthreads();
+#endif
+}
+
+// per-ray constants of the classification: M1 >= |v - o| for every vertex v of the classified rectangles
+struct RayBound { float m1_scaled, m1_sq; };   // 2^-15 M1, M1^2
+KYD_DEV RayBound ray_bound(const Ray& r)
+{
+    const float3 c = c_scene.bound_center;
+    const float M1 = (fabsf(r.o.x - c.x) + fabsf(r.o.y - c.y)) + (fabsf(r.o.z - c.z) + c_scene.bound_l1);
+    RayBound b;
+    b.m1_scaled = 0x1p-15f * M1;
+    b.m1_sq = M1 * M1;
+    return b;
+}
+
+template <int AXIS> KYD_DEV float comp(float3 v) { return AXIS == 0 ? v.x : AXIS == 1 ? v.y : v.z; }
+
+// The decision from the approximate plane distance t, the approximate in-plane coordinates (u, v), |1 / (d.n)| and the
+// rectangle's 2^-15 / area: sets bit `bit` of cand (phase 2 needed), inside (edge functions settled) and -- CERTAIN --
+// certain (hit inside (eps, t_hi) without phase 2).  NaN / infinite inputs make every comparison false: candidate.
+template <bool CERTAIN>
+KYD_DEV void rect_decide(float t, float u, float v, float ard, float c_area, const RayBound& rb, float t_hi, unsigned bit,
+                         unsigned& cand, unsigned& inside, unsigned& certain)
+{
+    const float m = (c_area * rb.m1_sq) * ard;
+    const float tau = __fmaf_rn(0x1p-18f, fabsf(t), rb.m1_scaled * ard);
+    const float lo = fminf(fminf(u, v), fminf(1.f - u, 1.f - v));
+    // (fminf drops a NaN operand; a NaN among u, v needs an infinite intermediate, which makes m infinite or NaN as well)
+    const bool out = (t < KYD_SHAPE_EPSILON - tau) || (t > t_hi + tau) || (lo < -m);
+    const bool in = lo > m;
+    if (CERTAIN)
+    {
+        const bool sure = in && (t > KYD_SHAPE_EPSILON + tau) && (t < t_hi - tau);
+        certain |= sure ? bit : 0u;
+        cand |= (out || sure) ? 0u : bit;
+    }
+    else
+        cand |= out ? 0u : bit;
+    inside |= in ? bit : 0u;
+}
+
+template <int AXIS, bool CERTAIN>
+KYD_DEV void rects_phase1_aligned(const Ray& r, const RayBound& rb, float t_hi, int begin, int end, unsigned& cand, unsigned& inside, unsigned& certain)
+{
+    constexpr int B = (AXIS + 1) % 3, C = (AXIS + 2) % 3;
+    const float oa = comp<AXIS>(r.o), ob = comp<B>(r.o), oc = comp<C>(r.o);
+    const float db = comp<B>(r.d), dc = comp<C>(r.d);
+    float rd;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(comp<AXIS>(r.d)));
+    const float ard = fabsf(rd);
+    for (int k = begin; k < end; ++k)
+    {
+        const RectAligned& c = c_scene.rect_aligned[k];
+        const float t = (c.pa - oa) * rd;
+        const float u = c.gb * __fmaf_rn(t, db, ob - c.lo_b);
+        const float v = c.gc * __fmaf_rn(t, dc, oc - c.lo_c);
+        rect_decide<CERTAIN>(t, u, v, ard, c.c_area, rb, t_hi, 1u << k, cand, inside, certain);
+    }
+}
+
+template <bool CERTAIN>
+KYD_DEV void rects_phase1_general(const Ray& r, const RayBound& rb, float t_hi, int first_bit, int count, unsigned& cand, unsigned& inside, unsigned& certain)
+{
+    for (int j = 0; j < count; ++j)
+    {
+        const RectCull& c = c_scene.rect_general[j];
+        const float obx = c.b.x - r.o.x, oby = c.b.y - r.o.y, obz = c.b.z - r.o.z;
+        const float N = __fmaf_rn(c.n.z, obz, __fmaf_rn(c.n.y, oby, c.n.x * obx));
+        const float D = __fmaf_rn(c.n.z, r.d.z, __fmaf_rn(c.n.y, r.d.y, c.n.x * r.d.x));
+        float rd;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(D));
+        const float t = N * rd;
+        const float qx = __fmaf_rn(t, r.d.x, -obx), qy = __fmaf_rn(t, r.d.y, -oby), qz = __fmaf_rn(t, r.d.z, -obz);
+        const float u = __fmaf_rn(c.gu.z, qz, __fmaf_rn(c.gu.y, qy, c.gu.x * qx));
+        const float v = __fmaf_rn(c.gv.z, qz, __fmaf_rn(c.gv.y, qy, c.gv.x * qx));
+        rect_decide<CERTAIN>(t, u, v, fabsf(rd), c.c_area, rb, t_hi, 1u << (first_bit + j), cand, inside, certain);
+    }
+}
+
+// the reference's edge functions on the staged copy of a rectangle (ky.cpp:1265-1281)
+KYD_DEV bool rect_edges_exact(const float* s, const Ray& r)
+{
+    const float3 oa = sub(V3(s[0], s[1], s[2]), r.o), ob = sub(V3(s[3], s[4], s[5]), r.o);
+    const float3 oc = sub(V3(s[6], s[7], s[8]), r.o), od = sub(V3(s[9], s[10], s[11]), r.o);
+    const float v0d = dot(cross(oc, ob), r.d);
+    const float v1d = dot(cross(ob, oa), r.d);
+    const float v2d = dot(cross(oa, od), r.d);
+    const float v3d = dot(cross(od, oc), r.d);
+    return ((v0d < 0.f) && (v1d < 0.f) && (v2d < 0.f) && (v3d < 0.f)) || ((v0d >= 0.f) && (v1d >= 0.f) && (v2d >= 0.f) && (v3d >= 0.f));
+}
+
+KYD_DEV float rect_t_exact(const float* s, const Ray& r) // ky.cpp:1283
+{
+    const float3 n = V3(s[12], s[13], s[14]);
+    return dot(n, sub(V3(s[0], s[1], s[2]), r.o)) / dot(n, r.d);
+}
+
+// phase 1 over the classified rectangles: bit k of `cand` = rectangle k needs phase 2, of `inside` = its edge functions are
+// settled, of `certain` (CERTAIN only) = it is certainly hit inside (eps, t_hi) and needs no phase 2
+template <bool CERTAIN>
+KYD_DEV void rects_phase1(const Ray& r, float t_hi, unsigned& cand, unsigned& inside, unsigned& certain)
+{
+    cand = inside = certain = 0u;
+    const RayBound rb = ray_bound(r);
+    const int e0 = c_scene.rect_aligned_end[0], e1 = c_scene.rect_aligned_end[1], e2 = c_scene.rect_aligned_end[2];
+    rects_phase1_aligned<0, CERTAIN>(r, rb, t_hi, 0, e0, cand, inside, certain);
+    rects_phase1_aligned<1, CERTAIN>(r, rb, t_hi, e0, e1, cand, inside, certain);
+    rects_phase1_aligned<2, CERTAIN>(r, rb, t_hi, e1, e2, cand, inside, certain);
+    rects_phase1_general<CERTAIN>(r, rb, t_hi, e2, c_scene.n_rect_general, cand, inside, certain);
+}
+
+// rectangles beyond the 32 the masks hold: the list walk's own test
+template <int MODE>
+KYD_DEV bool rects_overflow(const Ray& r, float& tmax, int& best, int light_surface)
+{
+    bool found = false;
+    const int end = c_scene.kind_end[0];
+    for (int k = 32; k < end; ++k)   // (the classifiers cover the first 32 rectangles of the sorted copy)
+    {
+        float t;
+        if (shape_hit_candidate<KYD_SHAPE_RECTANGLE>(c_scene.sorted_shape[k], r, &t))
+        {
+            const int surface = c_scene.sorted_surface[k];
+            if (MODE == 0) { if (t < tmax || (t == tmax && surface < best)) { tmax = t; best = surface; } }
+            else if (MODE == 1) { if (t < r.tmax) found = true; }
+            else if (surface != light_surface && (t < r.tmax || (t == r.tmax && surface < light_surface))) found = true;
+        }
+    }
+    return found;
+}
+
+// scene_t::intersect (ky.cpp:3172-3184): closest hit, lowest surface index among equal distances
+KYD_DEV int scene_closest_2p(const Ray& r, float* out_t)
+{
+    float tmax = r.tmax;
+    int best = -1;
+    scene_closest_kind<1, KYD_SHAPE_SPHERE>(r, tmax, best);
+    unsigned cand, inside, certain;
+    rects_phase1<false>(r, tmax, cand, inside, certain);
+    if (!(r.tmax > KYD_SHAPE_EPSILON))
+        cand = 0u;   // a null ray (idle lane): nothing to resolve
+    const float* sm = rect_smem();
+    while (cand != 0u)
+    {
+        const int k = __ffs(cand) - 1;
+        cand &= cand - 1u;
+        const float* s = sm + k * KYD_RECT_SMEM_STRIDE;
+        const float t = rect_t_exact(s, r);
+        const int surface = __float_as_int(s[15]);
+        if ((t > KYD_SHAPE_EPSILON) && (t < tmax || (t == tmax && surface < best)))
+        {
+            bool hit = ((inside >> k) & 1u) != 0u;
+            if (!hit)
+                hit = rect_edges_exact(s, r);
+            if (hit)
+            {
+                tmax = t;
+                best = surface;
+            }
+        }
+    }
+    rects_overflow<0>(r, tmax, best, -1);
+    scene_closest_kind<2, KYD_SHAPE_TRIANGLE>(r, tmax, best);
+    scene_closest_kind<3, KYD_SHAPE_DISK>(r, tmax, best);
+    *out_t = tmax;
+    return best;
+}
+
+// scene_t::occluded's question (ky.cpp:3187-3206): is any surface hit inside (epsilon, r.tmax)?  Every lane may call it;
+// a lane without a query passes r.tmax < 0.
+KYD_DEV bool scene_any_hit_2p(const Ray& r)
+{
+    const bool live = r.tmax > KYD_SHAPE_EPSILON;
+    bool hit = scene_any_hit_kind_uniform<1, KYD_SHAPE_SPHERE>(r, false);
+    unsigned cand, inside, certain;
+    rects_phase1<true>(r, r.tmax, cand, inside, certain);
+    hit = hit || certain != 0u;
+    if (!live || hit)
+        cand = 0u;
+    const float* sm = rect_smem();
+    while (cand != 0u)
+    {
+        const int k = __ffs(cand) - 1;
+        cand &= cand - 1u;
+        const float* s = sm + k * KYD_RECT_SMEM_STRIDE;
+        const float t = rect_t_exact(s, r);
+        if ((t > KYD_SHAPE_EPSILON) && (t < r.tmax) && ((((inside >> k) & 1u) != 0u) || rect_edges_exact(s, r)))
+        {
+            hit = true;
+            cand = 0u;
+        }
+    }
+    float tm = r.tmax;
+    int b = -1;
+    hit = rects_overflow<1>(r, tm, b, -1) || hit;
+    hit = scene_any_hit_kind_uniform<2, KYD_SHAPE_TRIANGLE>(r, hit);
+    hit = scene_any_hit_kind_uniform<3, KYD_SHAPE_DISK>(r, hit);
+    return hit && live;
+}
+
+// occlusion form of the BSDF-sampled query (scene_blocked_before): any surface other than light_surface that the list walk
+// would prefer to it -- closer, or as close with a lower index?  r.tmax = distance of light_surface; lanes without a query pass
+// light_surface < 0.
+KYD_DEV bool scene_blocked_before_2p(const Ray& r, int light_surface)
+{
+    const bool live = light_surface >= 0;
+    bool blocked = scene_blocked_before_kind_uniform<1, KYD_SHAPE_SPHERE>(r, light_surface, false);
+    unsigned cand, inside, certain;
+    rects_phase1<true>(r, r.tmax, cand, inside, certain);
+    const float* sm = rect_smem();
+    // certainly hit before r.tmax: blocks unless it is the light's own surface (whose t equals r.tmax: never "certain", but
+    // the check costs nothing)
+    for (unsigned c = certain; c != 0u && live && !blocked; c &= c - 1u)
+        if (__float_as_int(sm[(__ffs(c) - 1) * KYD_RECT_SMEM_STRIDE + 15]) != light_surface)
+            blocked = true;
+    if (!live || blocked)
+        cand = 0u;
+    while (cand != 0u)
+    {
+        const int k = __ffs(cand) - 1;
+        cand &= cand - 1u;
+        const float* s = sm + k * KYD_RECT_SMEM_STRIDE;
+        const int surface = __float_as_int(s[15]);
+        if (surface == light_surface)
+            continue;
+        const float t = rect_t_exact(s, r);
+        if ((t > KYD_SHAPE_EPSILON) && (t < r.tmax || (t == r.tmax && surface < light_surface)) &&
+            ((((inside >> k) & 1u) != 0u) || rect_edges_exact(s, r)))
+        {
+            blocked = true;
+            cand = 0u;
+        }
+    }
+    float tm = r.tmax;
+    int b = -1;
+    blocked = (live && rects_overflow<2>(r, tm, b, light_surface)) || blocked;
+    blocked = scene_blocked_before_kind_uniform<2, KYD_SHAPE_TRIANGLE>(r, light_surface, blocked);
+    blocked = scene_blocked_before_kind_uniform<3, KYD_SHAPE_DISK>(r, light_surface, blocked);
+    return blocked && live;
+}
+#else
+KYD_DEV void stage_rects() {}
+#endif // !KYD_BIG_SCENE
+
+// the queries of the wavefront kernels: two-phase traversal for scenes in constant memory, else the list walk / hierarchy
+KYD_DEV int wf_closest(const Ray& r, float* out_t)
+{
+#if KYD_TWO_PHASE && !KYD_BIG_SCENE
+    return scene_closest_2p(r, out_t);
+#else
+    return scene_closest(r, out_t);
+#endif
+}
+KYD_DEV bool wf_any_hit(const Ray& r)            // callable by all lanes (r.tmax < 0: no query)
+{
+#if KYD_TWO_PHASE && !KYD_BIG_SCENE
+    return scene_any_hit_2p(r);
+#else
+    return scene_any_hit_uniform(r);
+#endif
+}
+KYD_DEV bool wf_blocked_before(const Ray& r, int light_surface)   // callable by all lanes (light_surface < 0: no query)
+{
+#if KYD_TWO_PHASE && !KYD_BIG_SCENE
+    return scene_blocked_before_2p(r, light_surface);
+#else
+    return scene_blocked_before_uniform(r, light_surface);
+#endif
+}
+
 KYD_DEV float3 areal_radiance(const DevLight& l, float3 light_normal, float3 wo) // ky.cpp:2957-2960
 {
     return (dot(light_normal, wo) > 0) ? l.color : KYD_BLACK;

@@ -17,6 +17,7 @@ struct DevCounters
     unsigned long long rays_traced; // scene queries actually traversed on the device
     unsigned long long queue[16];   // wavefront queue tails (layout: kyd_wavefront.cuh)
     unsigned long long shade_vertices, shade_lines; // wavefront shade: vertices shaded, light-sampling lines written
+    unsigned long long intersect_rays;              // closest-hit queries traversed by k_intersect (its share of rays_traced)
 };
 
 // wavefront buffers (device memory owned by the context), capacity = paths per wave
@@ -64,6 +65,7 @@ void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 void launch_sum_partials(float* film_dev, const float* const* parts, int n_parts, int64_t n, bool clamp, int sm_count, cudaStream_t stream);
 
 void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
+void launch_selftest_traversal(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 
 // film output stage (kyd_film.cu): float film -> body bytes of `format` (kyd_film_format); film_dev 16-byte and

@@ -495,6 +495,102 @@ __global__ void k_selftest_pow(unsigned long long first, unsigned long long coun
     if (slow) atomicAdd(&out[1], slow);
 }
 
+// two-phase traversal against the list walk on the uploaded scene: adversarial rays -- between points of two surfaces, the
+// points snapped to within 2^-5 .. 2^-30 of edges and corners half of the time, origins on or just off their surface, random
+// and grazing directions -- and for each the three queries with limits that sit exactly on hit distances.
+// out[0] = queries whose answers differ, out[1] = rays whose closest-hit query hit something (the test is not vacuous)
+KYD_DEV float3 selftest_surface_point(int surface, unsigned long long h, float3* normal)
+{
+    const DevShape& sh = c_scene.surf_shape[surface];
+    float u = (float)(unsigned)(h >> 40) * 0x1p-24f, v = (float)(unsigned)((h >> 16) & 0xffffffu) * 0x1p-24f;
+    const unsigned snap = (unsigned)h & 15u;
+    if (snap & 1u) { const float e = ldexpf((snap & 4u) ? 1.f : -1.f, -5 - (int)((h >> 8) % 26u)); u = ((h >> 4) & 1u) ? 1.f + e : e; }
+    if (snap & 2u) { const float e = ldexpf((snap & 8u) ? 1.f : -1.f, -5 - (int)((h >> 12) % 26u)); v = ((h >> 5) & 1u) ? 1.f + e : e; }
+    *normal = sh.n;
+    if (sh.kind == KYD_SHAPE_SPHERE)
+    {
+        const float3 dir = uniform_sphere_sample(make_float2(fminf(fmaxf(u, 0.f), 1.f), fminf(fmaxf(v, 0.f), 1.f)));
+        *normal = dir;
+        return add(sh.p0, mul(dir, sh.radius));
+    }
+    if (sh.kind == KYD_SHAPE_DISK)
+    {
+        const Frame f = frame_from_z(sh.n);
+        return add(sh.p0, mul(add(mul(f.s, 2.f * u - 1.f), mul(f.t, 2.f * v - 1.f)), sh.radius * 0.75f));
+    }
+    // rectangle: the parallelogram p1 + u (p0 - p1) + v (p2 - p1); triangle: the same, folded
+    if (sh.kind == KYD_SHAPE_TRIANGLE && u + v > 1.f) { u = 1.f - u; v = 1.f - v; }
+    return add(add(sh.p1, mul(sub(sh.p0, sh.p1), u)), mul(sub(sh.p2, sh.p1), v));
+}
+
+__global__ void __launch_bounds__(256) k_selftest_traversal(unsigned long long first, unsigned long long count, unsigned long long* __restrict__ out)
+{
+    stage_rects();
+    unsigned long long bad = 0, hits = 0;
+    const int n = c_scene.n_surfaces;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count && n > 0; i += stride)
+    {
+        const unsigned long long h0 = mix64(first + i), h1 = mix64(h0 ^ 0x9E3779B97F4A7C15ull), h2 = mix64(h1 + 0x632BE59BD9B4E019ull);
+        const int s1 = (int)((h0 >> 8) % (unsigned)n), s2 = (int)((h0 >> 32) % (unsigned)n);
+        float3 n1, n2;
+        const float3 a = selftest_surface_point(s1, h1, &n1);
+        const float3 b = selftest_surface_point(s2, h2, &n2);
+        Ray r;
+        const unsigned mode = (unsigned)h0 & 7u;
+        float3 dir = sub(b, a);
+        if (mode == 6u)
+            dir = uniform_sphere_sample(make_float2((float)(unsigned)(h2 >> 40) * 0x1p-24f, (float)(unsigned)(h1 >> 40) * 0x1p-24f));
+        if (mode == 7u)   // grazing: almost inside the plane of the first surface
+            dir = add(cross(n1, sub(b, a)), mul(n1, ldexpf(1.f, -3 - (int)((h0 >> 56) % 24u))));
+        if (!(msq(dir) > 0.f))
+            dir = V3(0.f, 0.f, 1.f);
+        r.d = normalize(dir);
+        r.o = (mode & 1u) ? offset_ray_origin(a, normalize(n1), r.d) : a;
+        r.tmax = KYD_INF;
+
+        float t0, t1;
+        const int c0 = scene_closest(r, &t0), c1 = scene_closest_2p(r, &t1);
+        if (c0 != c1 || (c0 >= 0 && __float_as_uint(t0) != __float_as_uint(t1)))
+            ++bad;
+        if (c0 >= 0)
+            ++hits;
+        // occlusion queries: the shadow-ray limit, and limits on and next to the closest hit's distance
+        const float limits[4] = { distance(r.o, b) - 2e-3f, t0, c0 >= 0 ? __uint_as_float(__float_as_uint(t0) + 1u) : 1.f,
+                                  c0 >= 0 ? t0 * ((float)(unsigned)(h2 & 0xffffu) * 0x1p-16f) : 0.5f };
+        for (int k = 0; k < 4; ++k)
+        {
+            Ray q = r;
+            q.tmax = limits[k];
+            if (scene_any_hit(q) != scene_any_hit_2p(q))
+                ++bad;
+        }
+        // occlusion form of a BSDF-sampled query: towards the closest hit's surface, and towards the second surface if the ray hits it
+        if (c0 >= 0)
+        {
+            Ray q = r;
+            q.tmax = t0;
+            if (scene_blocked_before(q, c0) != scene_blocked_before_2p(q, c0))
+                ++bad;
+        }
+        float t2;
+        if (shape_hit_distance(c_scene.surf_shape[s2], r, KYD_INF, &t2))
+        {
+            Ray q = r;
+            q.tmax = t2;
+            if (scene_blocked_before(q, s2) != scene_blocked_before_2p(q, s2))
+                ++bad;
+        }
+    }
+    if (bad) atomicAdd(&out[0], bad);
+    if (hits) atomicAdd(&out[1], hits);
+}
+
+void launch_selftest_traversal(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream)
+{
+    k_selftest_traversal<<<148 * 8, 256, 0, stream>>>(first, count, out_dev);
+}
+
 void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream)
 {
     k_selftest_pow<<<148 * 16, 256, 0, stream>>>(first, count, out_dev);

@@ -53,6 +53,25 @@ struct BvhNode
     int count;
 };
 
+// Conservative classifiers of the rectangles (kyd_device.cuh, "two-phase traversal"), precomputed in double at upload.
+// General form: the rectangle as the parallelogram b + u eu + v ev in its plane.  A rectangle whose four points are not a
+// planar parallelogram to 2^-20 of its diagonal gets n = 0: its classification is always "candidate", i.e. every ray
+// takes the reference's own test.
+struct RectCull
+{
+    float3 b; float c_area;    // corner p1; 2^-15 / area
+    float3 n; int pad0;        // unit normal (0: exact test only)
+    float3 gu; int pad1;       // dual basis: u = gu . (p - b), v = gv . (p - b)
+    float3 gv; int pad2;
+};
+// Axis-aligned form (every Cornell wall): normal along axis A, the rectangle spans [lo_b, lo_b + 1/gb] x [lo_c, lo_c + 1/gc]
+// along axes B = (A + 1) % 3 and C = (A + 2) % 3 in the plane x_A = pa
+struct RectAligned
+{
+    float pa, lo_b, lo_c, gb;
+    float gc, c_area; int pad0, pad1;
+};
+
 struct DevScene
 {
     DevCamera camera;
@@ -71,6 +90,15 @@ struct DevScene
     DevShape sorted_shape[KYD_MAX_SURFACES];
     int sorted_surface[KYD_MAX_SURFACES];   // surface index of sorted_shape[k]
     int kind_end[4];                        // sorted_shape[kind_end[g-1] .. kind_end[g]) is group g
+    // two-phase traversal: the first n_rect_cull = min(kind_end[0], 32) rectangles of the sorted copy, regrouped as
+    // aligned-x | aligned-y | aligned-z | general; bit k of the traversal's masks is position k of that order
+    RectAligned rect_aligned[32];           // positions [0, rect_aligned_end[2])
+    RectCull rect_general[32];              // positions rect_aligned_end[2] + j, j < n_rect_general
+    int rect_aligned_end[3];                // aligned rectangles with normal axis x: [0, end[0]); y: [end[0], end[1]); z: [end[1], end[2])
+    int n_rect_general;
+    int n_rect_cull;                        // = rect_aligned_end[2] + n_rect_general
+    int rect_order[32];                     // sorted_shape index of position k
+    float3 bound_center; float bound_l1;    // every vertex v of those rectangles: |v - bound_center|_1 <= bound_l1
     // large scenes (more than KYD_MAX_SURFACES surfaces): per-surface data and the hierarchy in global memory, the arrays
     // above unused; null pointers otherwise
     const DevShape* big_shape;

@@ -282,6 +282,7 @@ KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 template <bool CAMERA>
 __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
+    stage_rects();
     const int parity = bounce & 1;
     const int n = CAMERA ? wp.nslots : (int)counters->queue[Q_RAY0 + parity];
     if (!CAMERA && blockIdx.x == 0 && threadIdx.x < 9)
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(Wav
         r.d = V3(d.x, d.y, d.z);
         r.tmax = slot_cur >= 0 ? KYD_INF : -1.f; // extension rays are unbounded (ky.cpp:585, 665-668)
         float t;
-        const int s = scene_closest(r, &t);
+        const int s = wf_closest(r, &t);
         if (slot_cur >= 0)
         {
             float4* p = path_line(w, slot);
@@ -390,6 +391,9 @@ __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(Wav
     }
     push.commit(lobe_queues);
     flush_counters(rays, rays, counters);
+    rays = __reduce_add_sync(0xffffffffu, rays);
+    if ((threadIdx.x & 31) == 0 && rays)
+        atomicAdd(&counters->intersect_rays, (unsigned long long)rays);
 }
 
 // draws consumed by sample_all_light before light l (ky.cpp:3864-3869, 3900)
@@ -457,12 +461,19 @@ KYD_DEV float3 nee_resolve_pair(int ds, const NeeRay& qb, const NeeRay& ql, Shad
     float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
     if (qb.active)
     {
-        Lb = nee_bsdf_trace(qb);
+        if (qb.light_surface >= 0)
+            Lb = wf_blocked_before(qb.ray, qb.light_surface) ? KYD_BLACK : qb.value;
+        else
+        {
+            float t;
+            const int s = wf_closest(qb.ray, &t);
+            Lb = nee_bsdf_resolve(qb, s, t);
+        }
         counts->traced++;
     }
     if (ql.active)
     {
-        Ll = scene_any_hit(ql.ray) ? KYD_BLACK : ql.value;
+        Ll = wf_any_hit(ql.ray) ? KYD_BLACK : ql.value;
         counts->traced++;
     }
     if (ds == KYD_DS_BOTH_MIS)
@@ -638,6 +649,8 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
 template <int LOBE, int TRAITS, bool HOT, int NL>
 KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
 {
+    if ((LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG) && HOT && NL == NL_ONE)
+        stage_rects();   // this kernel traces its vertices' light queries itself
     const int parity = bounce & 1;
     const int n = (int)counters->queue[Q_LOBE0 + 4 * parity + LOBE];
     const int* __restrict__ queue = w.queue_lobe[LOBE];
@@ -777,6 +790,7 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 template <bool PAIRS>
 __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
 {
+    stage_rects();
     const int n_lights = c_scene.n_lights;
     const int stride = gridDim.x * blockDim.x;
     const int ds = wp.rp.direct_sample;
@@ -840,7 +854,7 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
                 const bool occlusion_form = live && q.light_surface >= 0;
                 if (__any_sync(0xffffffffu, occlusion_form))
                 {
-                    const bool blocked = scene_blocked_before_uniform(q.ray, occlusion_form ? q.light_surface : -1);
+                    const bool blocked = wf_blocked_before(q.ray, occlusion_form ? q.light_surface : -1);
                     if (occlusion_form)
                         Lb = blocked ? KYD_BLACK : q.value;
                 }
@@ -849,7 +863,7 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
                     Ray r = q.ray;
                     if (occlusion_form) r.tmax = -1.f;
                     float t;
-                    const int s = scene_closest(r, &t);
+                    const int s = wf_closest(r, &t);
                     if (live && !occlusion_form)
                         Lb = nee_bsdf_resolve(q, s, t);
                 }
@@ -861,7 +875,7 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
                 r.o = V3(lo.x, lo.y, lo.z);
                 r.d = V3(ld.x, ld.y, ld.z);
                 r.tmax = lo.w;                    // < 0: no query, nothing can be hit
-                const bool occluded = scene_any_hit_uniform(r);
+                const bool occluded = wf_any_hit(r);
                 if (lo.w >= 0.f)
                 {
                     Ll = occluded ? KYD_BLACK : V3(lv.x, lv.y, lv.z);

@@ -18,12 +18,22 @@ def sample_range(spp, world, rank):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
-def reduce_film(partial, dst=0, group=None):
+def reduce_film(partial, dst=0, group=None, ordered=False):
     """Sums the ranks' partial films into rank `dst` and clamps there (ky.cpp:3726).  `partial` is a torch
-    tensor on the device the process group's backend works with; returns it (meaningful on `dst` only)."""
+    tensor on the device the process group's backend works with; returns it (meaningful on `dst` only).
+    `ordered`: gather the partial films and add them in rank order instead of one reduce -- the sum is then the same
+    bits whatever algorithm the backend's reduce would have picked (world_size films of memory on `dst`)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.reduce(partial, dst=dst, op=dist.ReduceOp.SUM, group=group)
         root = dist.get_rank(group) == dst
+        if ordered:
+            parts = [torch.empty_like(partial) for _ in range(dist.get_world_size(group))] if root else None
+            dist.gather(partial, parts, dst=dst, group=group)
+            if root:
+                partial.copy_(parts[0])
+                for p in parts[1:]:
+                    partial.add_(p)
+        else:
+            dist.reduce(partial, dst=dst, op=dist.ReduceOp.SUM, group=group)
     else:
         root = True
     if root:
@@ -32,7 +42,7 @@ def reduce_film(partial, dst=0, group=None):
     return partial
 
 
-def render_job(device, scene, desc, film, group=None, stream=None):
+def render_job(device, scene, desc, film, group=None, stream=None, ordered=False):
     """Renders this rank's share of `desc` (a whole-job kyd render desc: sample range (0, spp)) into the
     CUDA tensor `film` [h, w, 3] float32 and finishes the job with reduce_film().  `device` is a
     ky_b200.Device on the tensor's GPU with `scene` uploaded."""
@@ -44,7 +54,9 @@ def render_job(device, scene, desc, film, group=None, stream=None):
     local.sample_begin, local.sample_end = begin, end
     local.flags = desc.flags & ~(ky.FLAG_CLAMP | ky.FLAG_ACCUMULATE)
     if end > begin:
+        # (a context's own stream is a blocking stream: torch work queued on the default stream before this call -- the
+        # film's zero fill -- is complete before the render touches the film; handle 0 selects that stream)
         device.render_device(local, film.data_ptr(), stream if stream is not None else torch.cuda.current_stream().cuda_stream)
     else:
         film.zero_()
-    return reduce_film(film, 0, group)
+    return reduce_film(film, 0, group, ordered)

@@ -6,6 +6,11 @@
 #
 #   oracle/_ref/libky_ref_verbatim.so   reference + compile-only patches P1-P4
 #   oracle/_ref/libky_ref_det.so        + P5 (stateless plastic lobe draw) + crlibm_shim.c
+#   oracle/_ref/libky_ref_glibc.so      + P5, glibc's own float libm (no crlibm_shim): what the libm contract costs,
+#                                       measured by tests/test_libm_contract.py
+#   oracle/_ref/libsmallpt_kernel_ref.so       smallpt2pbrt/smallpt_kernel.cpp, CPU_RENDER configuration
+#   oracle/_ref/libsmallpt_kernel_cuda_ref.so  the same file as smallpt_kernel.cu compiles it (USE_CUDA): the reference's
+#                                       own CUDA kernel, built for sm_100a (timed beside kyd_render_smallpt_f64)
 #
 # No reference source is copied into the repository: the patched copy lives in oracle/_ref/.
 # The reference's own build system (CMake, MSVC presets) is not used.
@@ -56,6 +61,10 @@ gcc -O2 -fPIC -fno-builtin -fvisibility=hidden -c "$here/crlibm_shim.c" -o "$out
 g++ $CXXFLAGS -DKY_ORACLE_DETERMINISTIC -shared "$here/ref_addon.cpp" "$out/crlibm_shim.o" \
     -Wl,-Bsymbolic -o "$out/libky_ref_det.so"
 
+# the deterministic configuration on glibc's own float functions (sinf / cosf / sincosf / powf / acosf): same sampler, same
+# plastic lobe draw, stock libm -- the build a maintainer gets by dropping lcg48_sampler_t and P5 into the reference
+g++ $CXXFLAGS -DKY_ORACLE_DETERMINISTIC -shared "$here/ref_addon.cpp" -Wl,-Bsymbolic -o "$out/libky_ref_glibc.so"
+
 # ---- the FP64 smallpt of the teaching ladder: smallpt2pbrt/smallpt_kernel.cpp, CPU_RENDER ----
 #   S1  smallpt_kernel.cpp:440-  main() (MSVC-only fopen_s / errno_t, writes a ppm)  -> cut off
 #   S2  smallpt_kernel.cpp:417   per-row progress fprintf                            -> removed (I/O only)
@@ -64,5 +73,15 @@ cp "$ref/smallpt2pbrt/smallpt_kernel.cpp" "$src"
 patch1 S1 '/^int main(int argc, char\* argv\[\])/,$d' '^int main(int argc, char\* argv\[\])'
 patch1 S2 '/fprintf(stderr, "\\rRendering (%d spp) %5.2f%%"/d' 'fprintf(stderr, "\\rRendering (%d spp) %5.2f%%"'
 g++ -std=c++20 -O2 -ffp-contract=off -fopenmp -fPIC -w -I"$out" -shared "$here/smallpt_addon.cpp" -o "$out/libsmallpt_kernel_ref.so"
+
+# the reference's CUDA kernel (smallpt_kernel.cu = "#define USE_CUDA" + the same file), for sm_100a; the reference ships no
+# arch flags (smallpt2pbrt/CMakeLists.txt:22-25).  Same S1 cut; the GPU configuration has no progress print.
+if command -v nvcc >/dev/null 2>&1; then
+    src="$out/smallpt_kernel_cuda_ref.cu"
+    cp "$ref/smallpt2pbrt/smallpt_kernel.cpp" "$src"
+    patch1 S1 '/^int main(int argc, char\* argv\[\])/,$d' '^int main(int argc, char\* argv\[\])'
+    nvcc -std=c++20 -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -w -I"$out" -shared "$here/smallpt_cuda_addon.cu" \
+        -o "$out/libsmallpt_kernel_cuda_ref.so"
+fi
 
 echo "build_ref: built $(ls "$out"/*.so | tr '\n' ' ')"

@@ -6,6 +6,8 @@ variants = {
     "base": [],
     "cur": [],
     "imb3": ["-DKYD_INTERSECT_MIN_BLOCKS=3"],
+    "imb4": ["-DKYD_INTERSECT_MIN_BLOCKS=4"],
+    "onephase": ["-DKYD_TWO_PHASE=0"],
     "imb2": ["-DKYD_INTERSECT_MIN_BLOCKS=2"],
     "mb5": ["-DKYD_SHADE_MIN_BLOCKS=5"],
     "mb6": ["-DKYD_SHADE_MIN_BLOCKS=6"],

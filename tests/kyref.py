@@ -174,3 +174,23 @@ def smallpt_f64(width, height, samples_per_pixel):
     out = np.zeros((height, width, 3), np.float64)
     assert _smallpt.smallpt_ref_render(C.c_int(width), C.c_int(height), C.c_int(samples_per_pixel), out.ctypes.data_as(C.c_void_p)) == 0
     return out
+
+
+_smallpt_cuda = None
+
+
+def smallpt_cuda_available():
+    return os.path.exists(os.path.join(REF_DIR, "libsmallpt_kernel_cuda_ref.so"))
+
+
+def smallpt_cuda(width, height, samples_per_pixel):
+    """The reference's own CUDA kernel (smallpt_kernel.cu, built for sm_100a by oracle/ref/build_ref.sh): returns
+    (film[h, w, 3] float64 rows bottom-up, wall-clock seconds of its Device::Render).  Needs a GPU."""
+    global _smallpt_cuda
+    if _smallpt_cuda is None:
+        _smallpt_cuda = C.CDLL(os.path.join(REF_DIR, "libsmallpt_kernel_cuda_ref.so"))
+    out = np.zeros((height, width, 3), np.float64)
+    sec = C.c_double(0)
+    rc = _smallpt_cuda.smallpt_ref_cuda_render(C.c_int(width), C.c_int(height), C.c_int(samples_per_pixel), out.ctypes.data_as(C.c_void_p), C.byref(sec))
+    assert rc == 0
+    return out, sec.value

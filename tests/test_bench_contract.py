@@ -32,7 +32,42 @@ def test_product_arm_fails_loudly_without_a_gpu():
     assert out.stdout.strip() == ""
 
 
-def test_wave_count_helper():
+def test_workload_table_and_roofline_inputs():
     sys.path.insert(0, ROOT)
     import bench
-    assert bench.JOB_WAVES(2) == 1 and bench.JOB_WAVES(32) == 16
+    import ky_b200 as ky
+    wl = bench.workloads(ky)
+    assert sorted(wl) == ["C1", "C2", "C3", "C4", "C5"]
+    assert [len(wl[c]["panels"]) for c in ("C1", "C2", "C3", "C4", "C5")] == [1, 3, 1, 12, 1]
+    assert sum(p[2] * p[3] for p in wl["C4"]["panels"]) == 1920 * 1080
+    # 712 flop per ray in the Cornell default scene, 488 in the Veach scene, 144 in the smallpt scene
+    assert bench.flop_per_ray(ky.Scene(ky.SCENE_CORNELL, 8, 8, ky.CB_DEFAULT)) == 712
+    assert bench.flop_per_ray(ky.Scene(ky.SCENE_VEACH, 8, 8)) == 488
+    assert bench.flop_per_ray(ky.Scene(ky.SCENE_SMALLPT, 8, 8)) == 144
+
+
+def test_ncu_summary_must_describe_this_build(tmp_path, monkeypatch):
+    """The ncu figures the line quotes come from a committed capture; one that names kernels the library does not contain is refused."""
+    sys.path.insert(0, ROOT)
+    import bench
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    lib = tmp_path / "ky_b200" / "lib"
+    lib.mkdir(parents=True)
+    (lib / "libkyd.so").write_bytes(open(os.path.join(ROOT, "ky_b200", "lib", "libkyd.so"), "rb").read())
+    csrc = tmp_path / "ky_b200" / "csrc"
+    csrc.mkdir()
+    (csrc / "a.cu").write_text("x")
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    assert bench.ncu_summary() is None
+    doc = {"source_hash": bench.source_hash(), "kernel_symbols": ["k_intersect", "k_shade"], "kernels": {"k_shade<lambert>": {"dram_bytes": 1.0}}}
+    (prof / "r02_ncu_summary.json").write_text(json.dumps(doc))
+    got = bench.ncu_summary()
+    assert got["same_sources"] is True and got["kernels"]["k_shade<lambert>"]["dram_bytes"] == 1.0
+    (csrc / "a.cu").write_text("y")
+    assert bench.ncu_summary()["same_sources"] is False
+    doc["kernel_symbols"].append("k_no_such_kernel")
+    (prof / "r02_ncu_summary.json").write_text(json.dumps(doc))
+    import pytest
+    with pytest.raises(SystemExit):
+        bench.ncu_summary()

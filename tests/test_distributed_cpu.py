@@ -38,9 +38,11 @@ def _worker(rank, world, port, out):
     scene = ky.Scene(ky.SCENE_CORNELL, w, h)
     b, e = sample_range(spp, world, rank)
     part, _ = kyo.render(scene, ky.render_desc(w, h, spp, sample_begin=b, sample_end=e, flags=0))
-    film = reduce_film(torch.from_numpy(part))
+    film = reduce_film(torch.from_numpy(part.copy()))
+    ordered = reduce_film(torch.from_numpy(part.copy()), ordered=True)
     if rank == 0:
         np.save(out, film.numpy())
+        np.save(out + ".ordered.npy", ordered.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -61,3 +63,8 @@ def test_two_rank_split_reduce_clamp_equals_the_single_process_film(tmp_path):
     assert got.shape == want.shape
     assert np.all(np.abs(got - want) <= 2e-6 * np.maximum(1.0, np.abs(want)))
     assert (got >= 0).all() and (got <= 1).all()
+    # the rank-ordered sum: exactly clamp(partial_0 + partial_1), whatever the backend's reduce algorithm
+    from ky_b200.distributed import sample_range
+    parts = [kyo.render(scene, ky.render_desc(40, 30, 5, sample_begin=b, sample_end=e, flags=0))[0] for b, e in (sample_range(5, 2, 0), sample_range(5, 2, 1))]
+    expect = np.clip((parts[0] + parts[1]).astype(np.float32), 0.0, 1.0)
+    assert np.array_equal(np.load(out + ".ordered.npy").view(np.uint32), expect.view(np.uint32))
