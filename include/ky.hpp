@@ -16,11 +16,14 @@
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <concepts>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <format>
 #include <fstream>
 #include <limits>
 #include <memory>
@@ -31,6 +34,47 @@
 #include <vector>
 
 #include "kyd.h"
+
+// ---- host utilities the reference's entry points use (ky.cpp:34-165) -------------------------
+// Build configuration: the reference defines KY_DEBUG under MSVC's _DEBUG and KY_RELEASE otherwise (ky.cpp:36-40), and its
+// render_single_scene selects the real render under KY_RELEASE (ky.cpp:4688-4709).
+#if defined(_DEBUG)
+    #if !defined(KY_DEBUG)
+        #define KY_DEBUG
+    #endif
+#elif !defined(KY_RELEASE)
+    #define KY_RELEASE
+#endif
+
+namespace ky {
+// LOG(fmt, args...): std::format to stdout; LOG_ERROR additionally throws (the reference's error convention, ky.cpp:75-82)
+template <class... Ts>
+inline void log_message(std::format_string<Ts...> fmt, Ts&&... args)
+{
+    std::fputs(std::format(fmt, std::forward<Ts>(args)...).c_str(), stdout);
+}
+template <class... Ts>
+[[noreturn]] inline void log_error(std::format_string<Ts...> fmt, Ts&&... args)
+{
+    const std::string msg = std::format(fmt, std::forward<Ts>(args)...);
+    std::fputs(msg.c_str(), stdout);
+    throw std::runtime_error(msg);
+}
+// seconds a callable took.  Wall clock: the reference's clock() adds up the CPU time of all OpenMP threads (ky.cpp:156-163),
+// which says nothing about a render that runs on GPUs.
+inline float timing_seconds(std::invocable auto function)
+{
+    const auto start = std::chrono::steady_clock::now();
+    function();
+    return std::chrono::duration<float>(std::chrono::steady_clock::now() - start).count();
+}
+} // namespace ky
+#ifndef LOG
+    #define LOG(...) ::ky::log_message(__VA_ARGS__)
+#endif
+#ifndef LOG_ERROR
+    #define LOG_ERROR(...) ::ky::log_error(__VA_ARGS__)
+#endif
 
 namespace ky {
 

@@ -247,6 +247,22 @@ int kyd_get_stats(kyd_ctx* ctx, kyd_stats* out);
 enum kyd_selftest_kind { KYD_SELFTEST_RSQRT = 0, KYD_SELFTEST_POW = 1, KYD_SELFTEST_TRAVERSAL = 2 };
 int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64_t* out2);
 
+/* Device known-answer harness: runs n inputs through ONE device function of the path and returns what it computed, so that
+   fixtures generated from the reference (tests/golden/golden_kat.npz) pin the device functions one by one -- including branches
+   no film reaches.  Layouts (floats per item) are those of the oracle's test entry points (oracle/kyo.c):
+     KYD_KAT_SHAPE_INTERSECT        object = kyd_shape*     in 7 {o, d, tmax}            out 8 {hit, tmax, position, normal}   ky.cpp:1111-1393
+     KYD_KAT_SHAPE_SAMPLE_DIRECTION object = kyd_shape*     in 8 {p, n, u0, u1}          out 7 {lp, ln, pdf}                   ky.cpp:1028-1051, 1419-1501
+     KYD_KAT_SHAPE_PDF_DIRECTION    object = kyd_shape*     in 9 {p, n, wi}              out 1 pdf                             ky.cpp:1055-1090, 1503-1513
+     KYD_KAT_MATERIAL_BSDF          object = kyd_material*  in 14 {p, n, wo, wi, u0, u1} out 13 {sample f, wi, pdf, type; eval; pdf; is_delta}  ky.cpp:2147-2682
+     KYD_KAT_CAMERA_RAYS            uploaded scene          in 2 {px, py}                out 6 {o, d}                          ky.cpp:1884-1892
+     KYD_KAT_LIGHT_SAMPLE           uploaded scene, light `index`  in 11 {p, n, u0, u1, wi}  out 11 {position, wi, pdf, Li, pdf_Li(wi)}  ky.cpp:2810-3062
+     KYD_KAT_SAMPLER                seed `index`            in 4 {x, y, sample, -}       out 16 draws of the counter-seeded sampler
+   `traits` selects the instantiation the specialised shade kernels use (0: general; 1: rectangle area light; 2: sphere area
+   lights), for the functions that have one.  in / out are HOST pointers. */
+enum kyd_kat_kind { KYD_KAT_SHAPE_INTERSECT = 0, KYD_KAT_SHAPE_SAMPLE_DIRECTION = 1, KYD_KAT_SHAPE_PDF_DIRECTION = 2, KYD_KAT_MATERIAL_BSDF = 3,
+                    KYD_KAT_CAMERA_RAYS = 4, KYD_KAT_LIGHT_SAMPLE = 5, KYD_KAT_SAMPLER = 6 };
+int kyd_kat(kyd_ctx* ctx, int which, const void* object, int index, int traits, int n, const float* in, float* out);
+
 /* size in paths of one wavefront (0 = library default, 2^24; larger values are clamped to 2^24); tuning knob, results do
    not depend on it */
 int kyd_set_wave_paths(kyd_ctx* ctx, int64_t paths);

@@ -92,8 +92,13 @@ class EntryParams(C.Structure):
 
 
 KYD_SYMBOLS = ["kyd_create", "kyd_create_multi", "kyd_device_count", "kyd_destroy", "kyd_last_error", "kyd_upload_scene", "kyd_render",
-               "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest",
+               "kyd_render_device", "kyd_clamp_device", "kyd_get_stats", "kyd_set_wave_paths", "kyd_selftest", "kyd_kat",
                "kyd_film_body_bytes", "kyd_film_header", "kyd_film_encode", "kyd_film_encode_device", "kyd_render_smallpt_f64"]
+
+# kyd_kat_kind
+KAT_SHAPE_INTERSECT, KAT_SHAPE_SAMPLE_DIRECTION, KAT_SHAPE_PDF_DIRECTION, KAT_MATERIAL_BSDF = 0, 1, 2, 3
+KAT_CAMERA_RAYS, KAT_LIGHT_SAMPLE, KAT_SAMPLER = 4, 5, 6
+TRAITS_ANY, TRAITS_AREA_RECTANGLE, TRAITS_AREA_SPHERE = 0, 1, 2
 
 # kyd_film_format
 FILM_GAMMA8, FILM_BMP24, FILM_RGBE = 0, 1, 2
@@ -132,6 +137,7 @@ def kyd():
         l.kyd_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         l.kyd_set_wave_paths.argtypes = [C.c_void_p, C.c_int64]
         l.kyd_selftest.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]
+        l.kyd_kat.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         l.kyd_render_smallpt_f64.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         l.kyd_film_body_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         l.kyd_film_body_bytes.restype = C.c_int64
@@ -307,6 +313,17 @@ class Device:
         out = (C.c_uint64 * 2)()
         self._check(kyd().kyd_selftest(self._ctx, which, first, count, out))
         return int(out[0]), int(out[1])
+
+    def kat(self, which, inputs, obj=None, index=0, traits=0):
+        """Device known-answer harness (kyd_kat): one device function of the path on `inputs` [n, in_floats]."""
+        out_floats = {KAT_SHAPE_INTERSECT: 8, KAT_SHAPE_SAMPLE_DIRECTION: 7, KAT_SHAPE_PDF_DIRECTION: 1, KAT_MATERIAL_BSDF: 13,
+                      KAT_CAMERA_RAYS: 6, KAT_LIGHT_SAMPLE: 11, KAT_SAMPLER: 16}[which]
+        inputs = np.ascontiguousarray(inputs, np.float32)
+        n = inputs.shape[0]
+        out = np.zeros((n, out_floats) if out_floats > 1 else (n,), np.float32)
+        self._check(kyd().kyd_kat(self._ctx, which, C.byref(obj) if obj is not None else None, index, traits, n,
+                                  inputs.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def stats(self):
         s = Stats()

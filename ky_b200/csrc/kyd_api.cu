@@ -135,6 +135,19 @@ int download_film(kyd_ctx* ctx, const float* dev, float* pinned, float* host, si
     return KYD_OK;
 }
 
+DevMaterial convert_material(const kyd_material& m)
+{
+    DevMaterial o{};
+    o.kind = m.kind;
+    o.diffuse = f3(m.diffuse); o.specular = f3(m.specular); o.transmission = f3(m.transmission);
+    o.eta = m.eta; o.exponent = m.exponent;
+    o.p_diffuse = m.diffuse_probability; o.p_specular = m.specular_probability;
+    // color_t / float_t is three divisions (ky.cpp:231); IEEE on the host == IEEE on the device
+    o.plastic_lambert = make_float3(m.diffuse[0] / m.diffuse_probability, m.diffuse[1] / m.diffuse_probability, m.diffuse[2] / m.diffuse_probability);
+    o.plastic_phong = make_float3(m.specular[0] / m.specular_probability, m.specular[1] / m.specular_probability, m.specular[2] / m.specular_probability);
+    return o;
+}
+
 DevShape convert_shape(const kyd_shape& s)
 {
     DevShape d{};
@@ -348,9 +361,10 @@ int bind_scene(kyd_ctx* ctx, SceneSlot& slot, cudaStream_t stream)
 // bytes of wavefront state per path slot under `plan` (ensure_wave_buffers, kyd_kernels.cu)
 size_t wave_bytes_per_path(const WavefrontPlan& plan, int n_lights)
 {
-    size_t b = 64 + 8 * 4;                                   // path record, 2 ray queues + 4 lobe queues + 2 vertex queues
-    if (plan.nee) b += (size_t)n_lights * (128 + 2 * 4);      // light-sampling lines + pair queues
-    if (plan.split) b += 96;                                  // vertex records
+    size_t b = 64 + 12 * 4;                                  // path record, 2 ray queues + 2 x 4 lobe queues + 2 vertex queues
+    if (plan.nee && !plan.pair_kernel) b += (size_t)n_lights * (128 + 2 * 4);   // light-sampling lines + pair queues
+    if (plan.pair_kernel) b += (size_t)n_lights * 16;          // k_nee results
+    if (plan.split || plan.pair_kernel) b += 96;               // vertex records
     return b;
 }
 
@@ -382,7 +396,10 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         // Results do not depend on the wave size, so memory decides it where it is short (a GPU shared with other work,
         // many lights: 136 B per light and path): the default is capped by what is free now, and an allocation that
         // still fails is retried with half the wave down to 64 Ki paths.
-        if (ctx->wave.capacity < capacity || ctx->wave.max_lights < nee_lights || (plan.split && !ctx->wave.has_vertex))
+        const int nee_units = plan.pair_kernel ? 1 : 8;
+        const bool vertex = plan.split || plan.pair_kernel;
+        if (ctx->wave.capacity < capacity || ctx->wave.max_lights < nee_lights || (nee_lights > 0 && ctx->wave.nee_units < nee_units) ||
+            (vertex && !ctx->wave.has_vertex))
         {
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
@@ -393,7 +410,7 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
             }
             for (;;)
             {
-                const cudaError_t e = (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, nee_lights, plan.split);
+                const cudaError_t e = (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, nee_lights, nee_units, vertex);
                 if (e == cudaSuccess) break;
                 cudaGetLastError();   // clear the sticky-free allocation error
                 if (e != cudaErrorMemoryAllocation || capacity <= 65536)
@@ -746,14 +763,7 @@ int upload_scene_one(kyd_ctx* ctx, const kyd_scene_desc* sc)
     {
         const kyd_material& m = sc->materials[i];
         if (m.kind < 0 || m.kind > KYD_MAT_PLASTIC) return fail(ctx, KYD_ERR_INVALID, "unknown material kind");
-        DevMaterial& o = d.materials[i];
-        o.kind = m.kind;
-        o.diffuse = f3(m.diffuse); o.specular = f3(m.specular); o.transmission = f3(m.transmission);
-        o.eta = m.eta; o.exponent = m.exponent;
-        o.p_diffuse = m.diffuse_probability; o.p_specular = m.specular_probability;
-        // color_t / float_t is three divisions (ky.cpp:231); IEEE on the host == IEEE on the device
-        o.plastic_lambert = make_float3(m.diffuse[0] / m.diffuse_probability, m.diffuse[1] / m.diffuse_probability, m.diffuse[2] / m.diffuse_probability);
-        o.plastic_phong = make_float3(m.specular[0] / m.specular_probability, m.specular[1] / m.specular_probability, m.specular[2] / m.specular_probability);
+        d.materials[i] = convert_material(m);
     }
     d.n_nondelta_lights = 0;
     for (int i = 0; i < sc->light_count; ++i)
@@ -776,10 +786,13 @@ int upload_scene_one(kyd_ctx* ctx, const kyd_scene_desc* sc)
     // for every direction (ky.cpp:1509-1512) so that every BSDF-sampled query would otherwise be traced, in scenes with
     // several lights, where each traced query also costs a sector of a light-sampling line.  Elsewhere (one light:
     // queries are traced inside shade; rectangle lights: pdf_Li already tests the hit) the closest-hit form is as fast.
+    // A scene's single area light (whatever its shape) uses it as well: shade then traces both of a vertex' queries with ONE
+    // copy of the occlusion code, which matters more than the query's cost (the shade kernels are instruction-fetch bound).
     for (int l = 0; l < KYD_MAX_LIGHTS; ++l)
     {
-        const bool sphere_area = l < sc->light_count && sc->lights[l].kind == KYD_LIGHT_AREA && d.light_shape[l].kind == KYD_SHAPE_SPHERE;
-        if (!(sphere_area && sc->light_count > 1))
+        const bool area = l < sc->light_count && sc->lights[l].kind == KYD_LIGHT_AREA;
+        const bool sphere_area = area && d.light_shape[l].kind == KYD_SHAPE_SPHERE;
+        if (!((sphere_area && sc->light_count > 1) || (area && sc->light_count == 1 && !big)))
             d.light_surface[l] = -2;
     }
     if (big)
@@ -1167,6 +1180,66 @@ int kyd_selftest(kyd_ctx* ctx, int which, uint64_t first, uint64_t count, uint64
     KYD_CUDA(ctx, e);
     out2[0] = host[0];
     out2[1] = host[1];
+    return KYD_OK;
+}
+
+int kyd_kat(kyd_ctx* ctx, int which, const void* object, int index, int traits, int n, const float* in, float* out)
+{
+    if (!ctx) return KYD_ERR_INVALID;
+    static const int in_floats[7] = { 7, 8, 9, 14, 2, 11, 4 }, out_floats[7] = { 8, 7, 1, 13, 6, 11, 16 };
+    if (which < 0 || which > KYD_KAT_SAMPLER) return fail(ctx, KYD_ERR_INVALID, "unknown known-answer kind");
+    if (n < 0 || !in || !out) return fail(ctx, KYD_ERR_INVALID, "bad known-answer buffers");
+    if (traits < 0 || traits > 2) return fail(ctx, KYD_ERR_INVALID, "traits must be 0, 1 or 2");
+    const bool needs_object = which <= KYD_KAT_MATERIAL_BSDF, needs_scene = which == KYD_KAT_CAMERA_RAYS || which == KYD_KAT_LIGHT_SAMPLE;
+    if (needs_object && !object) return fail(ctx, KYD_ERR_INVALID, "known-answer kind needs a shape / material");
+    if (needs_scene && (!ctx->has_scene || ctx->scene.bvh_nodes)) return fail(ctx, KYD_ERR_NO_SCENE, "known-answer kind needs an uploaded scene of at most KYD_MAX_SURFACES surfaces");
+    if (which == KYD_KAT_LIGHT_SAMPLE && (index < 0 || index >= ctx->scene.n_lights)) return fail(ctx, KYD_ERR_INVALID, "light index out of range");
+    if (n == 0) return KYD_OK;
+    DevShape shape{};
+    DevMaterial material{};
+    if (which <= KYD_KAT_SHAPE_PDF_DIRECTION)
+    {
+        const kyd_shape* s = (const kyd_shape*)object;
+        if (s->kind < 0 || s->kind > KYD_SHAPE_DISK) return fail(ctx, KYD_ERR_INVALID, "unknown shape kind");
+        shape = convert_shape(*s);
+    }
+    else if (which == KYD_KAT_MATERIAL_BSDF)
+    {
+        const kyd_material* m = (const kyd_material*)object;
+        if (m->kind < 0 || m->kind > KYD_MAT_PLASTIC) return fail(ctx, KYD_ERR_INVALID, "unknown material kind");
+        material = convert_material(*m);
+    }
+    KYD_CUDA(ctx, cudaSetDevice(ctx->device));
+    float *in_dev = nullptr, *out_dev = nullptr;
+    const size_t in_bytes = sizeof(float) * in_floats[which] * (size_t)n, out_bytes = sizeof(float) * out_floats[which] * (size_t)n;
+    KYD_CUDA(ctx, cudaMalloc(&in_dev, in_bytes));
+    cudaError_t e = cudaMalloc(&out_dev, out_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in_dev, in, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out_dev, 0, out_bytes, ctx->stream);
+    int rc = KYD_OK;
+    if (e == cudaSuccess)
+    {
+        SceneSlot& slot = g_scene_slot[0][ctx->device & 63];
+        std::lock_guard<std::mutex> lock(slot.launch);
+        if (needs_scene) rc = bind_scene(ctx, slot, ctx->stream);
+        if (rc == KYD_OK)
+        {
+            launch_kat(which, shape, material, index, traits, n, in_dev, out_dev, ctx->stream);
+            e = cudaGetLastError();
+            if (needs_scene && slot.last_use)
+            {
+                cudaEventRecord(slot.last_use, ctx->stream);
+                slot.last_stream = ctx->stream;
+                slot.used = true;
+            }
+        }
+    }
+    if (e == cudaSuccess && rc == KYD_OK) e = cudaMemcpyAsync(out, out_dev, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(in_dev);
+    cudaFree(out_dev);
+    if (rc != KYD_OK) return rc;
+    KYD_CUDA(ctx, e);
     return KYD_OK;
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "kyd_scene.h"
@@ -25,6 +26,7 @@ struct WaveBuffers
 {
     int64_t capacity = 0;
     int max_lights = 0;           // lights the light-sampling buffer was sized for (0: not allocated)
+    int nee_units = 0;            // float4 units per (light, path slot) of that buffer: 8 = a 128-byte line, 1 = a k_nee result
     bool has_vertex = false;
     // layouts: kyd_wavefront.cuh
     float4* path = nullptr;       // one 64-byte record (4 float4) per path slot
@@ -33,7 +35,8 @@ struct WaveBuffers
     // queues of path slots
     int* queue_a = nullptr;        // ray queues (ping-pong by bounce parity)
     int* queue_b = nullptr;
-    int* queue_lobe[4] = {};       // hit paths sorted by BSDF lobe: Lambert, mirror, glass, Phong (LOBE_* order)
+    int* queue_lobe[2][4] = {};    // hit paths sorted by BSDF lobe: Lambert, mirror, glass, Phong (LOBE_* order); [bounce parity]:
+                                   // with the intersect stage fused into shade, shade reads one set while it fills the other
     int* queue_nee[2] = {};        // vertices for the stand-alone light-sample stage (split mode): Lambert, Phong
     int* queue_pair[2] = {};       // (vertex, light) pairs with a light-sampling line: slot | light << 24; capacity * lights entries
 };
@@ -65,6 +68,7 @@ void launch_clamp(float* film_dev, int64_t n, cudaStream_t stream);
 void launch_sum_partials(float* film_dev, const float* const* parts, int n_parts, int64_t n, bool clamp, int sm_count, cudaStream_t stream);
 
 void launch_selftest_pow(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
+void launch_kat(int which, const DevShape& shape, const DevMaterial& material, int index, int traits, int n, const float* in_dev, float* out_dev, cudaStream_t stream);
 void launch_selftest_traversal(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 void launch_selftest_rsqrt(unsigned long long first, unsigned long long count, unsigned long long* out_dev, cudaStream_t stream);
 
@@ -82,6 +86,9 @@ struct WavefrontPlan
     bool inline_queries;  // hot and one light: shade traces its own light queries (no light-sampling lines, no shadow stage)
     bool nee;             // the shadow stage runs (light-sampling lines are written)
     bool split;           // KYD_FLAG_SPLIT_LIGHT_SAMPLE: vertex records for the stand-alone light-sample kernel
+    bool pair_kernel;     // hot with several lights: the light loop runs in k_nee over (vertex, light) pairs (vertex records + 16-byte results)
+    bool fused;           // inline_queries and not KYD_FUSE_INTERSECT=0: shade also traces the path's next ray (closest hit, lobe
+                          // classification), so only the camera rays go through the intersect kernel
 };
 inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scene)
 {
@@ -92,13 +99,16 @@ inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scen
     p.hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG && !p.split && scene.bvh_nodes == nullptr;
     p.inline_queries = p.hot && scene.n_lights == 1;
     p.nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0 && !p.inline_queries;
+    p.pair_kernel = p.hot && p.nee;
+    static const bool fuse_enabled = !(getenv("KYD_FUSE_INTERSECT") && getenv("KYD_FUSE_INTERSECT")[0] == '0');
+    p.fused = p.inline_queries && fuse_enabled;
     return p;
 }
 
 void free_wave_buffers(WaveBuffers& w);
 // (re)allocates the wavefront buffers for `capacity` path slots; light-sampling lines for `nee_lights` lights (0: none
 // needed) and vertex records only if `vertex`; returns a cudaError_t
-int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool vertex);
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int nee_units, bool vertex);
 
 // wavefront path: path_tracing_iteration_t and direct_lighting_t.  Adds to `launches` the kernels it launched.
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,

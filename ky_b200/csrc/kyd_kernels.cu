@@ -3,6 +3,7 @@
 //
 // Compile with -fmad=false (see kyd_device.cuh).
 #include <cstdlib>
+#include <cstring>
 #include "kyd_internal.h"
 #include "kyd_device.cuh"
 #include "kyd_wavefront.cuh"
@@ -495,6 +496,122 @@ __global__ void k_selftest_pow(unsigned long long first, unsigned long long coun
     if (slow) atomicAdd(&out[1], slow);
 }
 
+// ---- known-answer harness: one device function of the path per launch, inputs and outputs in the layouts of the oracle's
+// kyo_* test entry points (oracle/kyo.c), so that tests/golden/golden_kat.npz -- generated from the reference build -- pins
+// the DEVICE functions one by one, including branches no film reaches (a shading point inside a sphere light, total internal
+// reflection, the disk's parallel-ray reject, the inf -> 0 pdf guards)
+template <int TRAITS>
+KYD_DEV void kat_light(int light, const float* a, float* o)
+{
+    HitGeom g;
+    g.position = V3(a[0], a[1], a[2]);
+    g.normal = V3(a[3], a[4], a[5]);
+    g.wo = V3(0.f, 0.f, 1.f);
+    const LightSample ls = light_sample_Li<TRAITS>(light, g, make_float2(a[6], a[7]));
+    o[0] = ls.position.x; o[1] = ls.position.y; o[2] = ls.position.z;
+    o[3] = ls.wi.x; o[4] = ls.wi.y; o[5] = ls.wi.z;
+    o[6] = ls.pdf; o[7] = ls.Li.x; o[8] = ls.Li.y; o[9] = ls.Li.z;
+    o[10] = light_pdf_Li<TRAITS>(light, g, V3(a[8], a[9], a[10]));
+}
+
+__global__ void k_kat(int which, DevShape shape, DevMaterial material, int index, int traits, int n, const float* __restrict__ in, float* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    switch (which)
+    {
+    case KYD_KAT_SHAPE_INTERSECT: // shape_t::intersect ky.cpp:1111-1393; in {o, d, tmax}, out {hit, tmax, position, normal}
+    {
+        const float* a = in + 7 * i;
+        Ray r;
+        r.o = V3(a[0], a[1], a[2]); r.d = V3(a[3], a[4], a[5]); r.tmax = a[6];
+        float t;
+        const bool hit = shape_hit_distance(shape, r, r.tmax, &t);
+        float* o = out + 8 * i;
+        o[0] = hit ? 1.f : 0.f;
+        o[1] = hit ? t : r.tmax;
+        HitGeom g;
+        g.position = g.normal = V3(0.f, 0.f, 0.f);
+        if (hit)
+            g = shape_hit_geom(shape, r, t);
+        o[2] = g.position.x; o[3] = g.position.y; o[4] = g.position.z;
+        o[5] = g.normal.x; o[6] = g.normal.y; o[7] = g.normal.z;
+        break;
+    }
+    case KYD_KAT_SHAPE_SAMPLE_DIRECTION: // ky.cpp:1028-1051, 1419-1501; in {p, n, u}, out {lp, ln, pdf}
+    {
+        const float* a = in + 8 * i;
+        float3 lp = V3(0.f, 0.f, 0.f), ln = lp;
+        float pdf = 0.f;
+        const float3 p = V3(a[0], a[1], a[2]), ns = V3(a[3], a[4], a[5]);
+        const float2 u = make_float2(a[6], a[7]);
+        if (traits == TRAITS_AREA_RECTANGLE) shape_sample_direction<TRAITS_AREA_RECTANGLE>(shape, p, ns, u, &lp, &ln, &pdf);
+        else if (traits == TRAITS_AREA_SPHERE) shape_sample_direction<TRAITS_AREA_SPHERE>(shape, p, ns, u, &lp, &ln, &pdf);
+        else shape_sample_direction<TRAITS_ANY>(shape, p, ns, u, &lp, &ln, &pdf);
+        float* o = out + 7 * i;
+        o[0] = lp.x; o[1] = lp.y; o[2] = lp.z; o[3] = ln.x; o[4] = ln.y; o[5] = ln.z; o[6] = pdf;
+        break;
+    }
+    case KYD_KAT_SHAPE_PDF_DIRECTION: // ky.cpp:1055-1090, 1503-1513; in {p, n, wi}, out pdf
+    {
+        const float* a = in + 9 * i;
+        const float3 p = V3(a[0], a[1], a[2]), ns = V3(a[3], a[4], a[5]), wi = V3(a[6], a[7], a[8]);
+        out[i] = traits == TRAITS_AREA_RECTANGLE ? shape_pdf_direction<TRAITS_AREA_RECTANGLE>(shape, p, ns, wi)
+               : traits == TRAITS_AREA_SPHERE ? shape_pdf_direction<TRAITS_AREA_SPHERE>(shape, p, ns, wi)
+               : shape_pdf_direction<TRAITS_ANY>(shape, p, ns, wi);
+        break;
+    }
+    case KYD_KAT_MATERIAL_BSDF: // material_t::scattering + bsdf_t::sample / eval / pdf, ky.cpp:2147-2682
+    {                           // in {p, n, wo, wi, u}, out {sample.f, sample.wi, sample.pdf, sample.type, eval, pdf, is_delta}
+        const float* a = in + 14 * i;
+        HitGeom g;
+        g.position = V3(a[0], a[1], a[2]); g.normal = V3(a[3], a[4], a[5]); g.wo = V3(a[6], a[7], a[8]);
+        Bsdf b;
+        material_scattering(material, g, &b);
+        const BsdfSample bs = bsdf_sample(b, g.wo, make_float2(a[12], a[13]));
+        const float3 wi = V3(a[9], a[10], a[11]);
+        const float3 f = bsdf_eval(b, g.wo, wi);
+        const float pdf = bsdf_pdf(b, g.wo, wi);
+        float* o = out + 13 * i;
+        o[0] = bs.f.x; o[1] = bs.f.y; o[2] = bs.f.z; o[3] = bs.wi.x; o[4] = bs.wi.y; o[5] = bs.wi.z;
+        o[6] = bs.pdf; o[7] = (float)bs.type; o[8] = f.x; o[9] = f.y; o[10] = f.z; o[11] = pdf;
+        o[12] = bsdf_is_delta(b.lobe) ? 1.f : 0.f;
+        break;
+    }
+    case KYD_KAT_CAMERA_RAYS: // camera_t::generate_ray ky.cpp:1884-1892 of the uploaded scene; in {px, py}, out {o, d}
+    {
+        const Ray r = generate_ray(in[2 * i], in[2 * i + 1]);
+        float* o = out + 6 * i;
+        o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z; o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z;
+        break;
+    }
+    case KYD_KAT_LIGHT_SAMPLE: // light_t::sample_Li / pdf_Li of light `index` of the uploaded scene, ky.cpp:2810-3062
+    {                          // in {p, n, u, wi}, out {position, wi, pdf, Li, pdf_Li(wi)}
+        if (traits == TRAITS_AREA_RECTANGLE) kat_light<TRAITS_AREA_RECTANGLE>(index, in + 11 * i, out + 11 * i);
+        else if (traits == TRAITS_AREA_SPHERE) kat_light<TRAITS_AREA_SPHERE>(index, in + 11 * i, out + 11 * i);
+        else kat_light<TRAITS_ANY>(index, in + 11 * i, out + 11 * i);
+        break;
+    }
+    case KYD_KAT_SAMPLER: // lcg48 stream of (seed = material.kind bits.., x, y, sample): in {x, y, sample, count<=16}, out 16 floats
+    {
+        const float* a = in + 4 * i;
+        Sampler smp;
+        smp.start(KYD_SAMPLER_LCG48, (unsigned long long)(unsigned)index, (int)a[0], (int)a[1], (int)a[2]);
+        for (int k = 0; k < 16; ++k)
+            out[16 * i + k] = smp.get_float();
+        break;
+    }
+    default:
+        break;
+    }
+}
+
+void launch_kat(int which, const DevShape& shape, const DevMaterial& material, int index, int traits, int n, const float* in_dev, float* out_dev, cudaStream_t stream)
+{
+    k_kat<<<(n + 127) / 128, 128, 0, stream>>>(which, shape, material, index, traits, n, in_dev, out_dev);
+}
+
 // two-phase traversal against the list walk on the uploaded scene: adversarial rays -- between points of two surfaces, the
 // points snapped to within 2^-5 .. 2^-30 of edges and corners half of the time, origins on or just off their surface, random
 // and grazing directions -- and for each the three queries with limits that sit exactly on hit distances.
@@ -550,7 +667,7 @@ __global__ void __launch_bounds__(256) k_selftest_traversal(unsigned long long f
         r.tmax = KYD_INF;
 
         float t0, t1;
-        const int c0 = scene_closest(r, &t0), c1 = scene_closest_2p(r, &t1);
+        const int c0 = scene_closest(r, &t0), c1 = scene_closest_2p(r, -1, &t1);
         if (c0 != c1 || (c0 >= 0 && __float_as_uint(t0) != __float_as_uint(t1)))
             ++bad;
         if (c0 >= 0)
@@ -564,6 +681,9 @@ __global__ void __launch_bounds__(256) k_selftest_traversal(unsigned long long f
             q.tmax = limits[k];
             if (scene_any_hit(q) != scene_any_hit_2p(q))
                 ++bad;
+            float tq;
+            if (q.tmax > KYD_SHAPE_EPSILON && scene_any_hit(q) != (scene_closest_2p(q, -1, &tq) >= 0))   // occlusion as a closest-hit walk
+                ++bad;
         }
         // occlusion form of a BSDF-sampled query: towards the closest hit's surface, and towards the second surface if the ray hits it
         if (c0 >= 0)
@@ -572,6 +692,9 @@ __global__ void __launch_bounds__(256) k_selftest_traversal(unsigned long long f
             q.tmax = t0;
             if (scene_blocked_before(q, c0) != scene_blocked_before_2p(q, c0))
                 ++bad;
+            float tq;
+            if (scene_blocked_before(q, c0) != (scene_closest_2p(q, c0, &tq) != c0))   // ... and from the light surface's own hit
+                ++bad;
         }
         float t2;
         if (shape_hit_distance(c_scene.surf_shape[s2], r, KYD_INF, &t2))
@@ -579,6 +702,9 @@ __global__ void __launch_bounds__(256) k_selftest_traversal(unsigned long long f
             Ray q = r;
             q.tmax = t2;
             if (scene_blocked_before(q, s2) != scene_blocked_before_2p(q, s2))
+                ++bad;
+            float tq;
+            if (scene_blocked_before(q, s2) != (scene_closest_2p(q, s2, &tq) != s2))
                 ++bad;
         }
     }
@@ -646,19 +772,21 @@ static cudaError_t alloc_array(T** p, size_t count)
 
 void free_wave_buffers(WaveBuffers& w)
 {
-    void* ptrs[] = { w.path, w.vertex, w.nee, w.queue_a, w.queue_b, w.queue_lobe[0], w.queue_lobe[1],
-                     w.queue_lobe[2], w.queue_lobe[3], w.queue_nee[0], w.queue_nee[1], w.queue_pair[0], w.queue_pair[1] };
+    void* ptrs[] = { w.path, w.vertex, w.nee, w.queue_a, w.queue_b, w.queue_lobe[0][0], w.queue_lobe[0][1], w.queue_lobe[0][2], w.queue_lobe[0][3],
+                     w.queue_lobe[1][0], w.queue_lobe[1][1], w.queue_lobe[1][2], w.queue_lobe[1][3],
+                     w.queue_nee[0], w.queue_nee[1], w.queue_pair[0], w.queue_pair[1] };
     for (void* p : ptrs)
         if (p) cudaFree(p);
     w = WaveBuffers{};
 }
 
-int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool vertex)
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int nee_units, bool vertex)
 {
-    if (w.capacity >= capacity && w.max_lights >= nee_lights && (w.has_vertex || !vertex))
+    if (w.capacity >= capacity && w.max_lights >= nee_lights && (nee_lights == 0 || w.nee_units >= nee_units) && (w.has_vertex || !vertex))
         return cudaSuccess;
     if (capacity < w.capacity) capacity = w.capacity;
     if (nee_lights < w.max_lights) nee_lights = w.max_lights;
+    if (nee_units < w.nee_units) nee_units = w.nee_units;
     vertex = vertex || w.has_vertex;
     free_wave_buffers(w);
     const size_t P = (size_t)capacity, L = (size_t)nee_lights;
@@ -666,11 +794,11 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool v
     auto ok = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     ok(alloc_array(&w.path, 4 * P));
     if (vertex) ok(alloc_array(&w.vertex, 6 * P));
-    if (L > 0) ok(alloc_array(&w.nee, 8 * L * P));
+    if (L > 0) ok(alloc_array(&w.nee, (size_t)nee_units * L * P));
     ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P));
-    for (int c = 0; c < 4; ++c) ok(alloc_array(&w.queue_lobe[c], P));
+    for (int c = 0; c < 8; ++c) ok(alloc_array(&w.queue_lobe[c >> 2][c & 3], P));
     for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_nee[c], P));
-    if (L > 0)
+    if (L > 0 && nee_units > 1)
         for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_pair[c], L * P));
     if (e != cudaSuccess)
     {
@@ -679,6 +807,7 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool v
     }
     w.capacity = capacity;
     w.max_lights = nee_lights;
+    w.nee_units = L > 0 ? nee_units : 0;
     w.has_vertex = vertex;
     return cudaSuccess;
 }
@@ -686,31 +815,38 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, bool v
 #endif // !KYD_BIG_SCENE
 
 // the mirror and glass kernels sample no lights: one instantiation serves both light counts
-template <int TRAITS, bool HOT, int NL>
+template <int TRAITS, bool HOT, int NL, bool FUSE>
 static void launch_shade_lobes(int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
 {
     constexpr int NL_SPECULAR = HOT ? NL_ONE : NL_ANY;
-    k_shade<LOBE_LAMBERT, TRAITS, HOT, NL><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
-    k_shade<LOBE_PHONG, TRAITS, HOT, NL><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
-    k_shade<LOBE_MIRROR, TRAITS, HOT, NL_SPECULAR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
-    k_shade<LOBE_FRESNEL, TRAITS, HOT, NL_SPECULAR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_LAMBERT, TRAITS, HOT, NL, FUSE><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_PHONG, TRAITS, HOT, NL, FUSE><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_MIRROR, TRAITS, HOT, NL_SPECULAR, FUSE><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade<LOBE_FRESNEL, TRAITS, HOT, NL_SPECULAR, FUSE><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
 }
 
-static void launch_shade(int traits, bool hot, bool one_light, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w,
+template <int TRAITS>
+static void launch_shade_one_light(bool fused, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
+{
+    if (fused) launch_shade_lobes<TRAITS, true, NL_ONE, true>(grid, stream, wp, w, counters, bounce);
+    else launch_shade_lobes<TRAITS, true, NL_ONE, false>(grid, stream, wp, w, counters, bounce);
+}
+
+static void launch_shade(int traits, bool hot, bool one_light, bool fused, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w,
                          DevCounters* counters, int bounce)
 {
-    if (!hot) launch_shade_lobes<TRAITS_ANY, false, NL_ANY>(grid, stream, wp, w, counters, bounce);
+    if (!hot) launch_shade_lobes<TRAITS_ANY, false, NL_ANY, false>(grid, stream, wp, w, counters, bounce);
 #if !KYD_BIG_SCENE
-    else if (traits == TRAITS_AREA_RECTANGLE) launch_shade_lobes<TRAITS_AREA_RECTANGLE, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
+    else if (traits == TRAITS_AREA_RECTANGLE) launch_shade_one_light<TRAITS_AREA_RECTANGLE>(fused, grid, stream, wp, w, counters, bounce);
     else if (traits == TRAITS_AREA_SPHERE)
     {
-        if (one_light) launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
-        else launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_MANY>(grid, stream, wp, w, counters, bounce);
+        if (one_light) launch_shade_one_light<TRAITS_AREA_SPHERE>(fused, grid, stream, wp, w, counters, bounce);
+        else launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_MANY, false>(grid, stream, wp, w, counters, bounce);
     }
     else
     {
-        if (one_light) launch_shade_lobes<TRAITS_ANY, true, NL_ONE>(grid, stream, wp, w, counters, bounce);
-        else launch_shade_lobes<TRAITS_ANY, true, NL_MANY>(grid, stream, wp, w, counters, bounce);
+        if (one_light) launch_shade_one_light<TRAITS_ANY>(fused, grid, stream, wp, w, counters, bounce);
+        else launch_shade_lobes<TRAITS_ANY, true, NL_MANY, false>(grid, stream, wp, w, counters, bounce);
     }
 #endif
 }
@@ -737,7 +873,21 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             all_rect = all_rect && area && scene.light_shape[l].kind == KYD_SHAPE_RECTANGLE;
             all_sphere = all_sphere && area && scene.light_shape[l].kind == KYD_SHAPE_SPHERE;
         }
-        traits = (all_rect && scene.n_lights == 1) ? TRAITS_AREA_RECTANGLE : all_sphere ? TRAITS_AREA_SPHERE : TRAITS_ANY;
+        // what the specialised kernels assume beyond the light kinds (kyd_device.cuh, nee_bsdf_from_sample): the BSDF-sampled
+        // query is in its occlusion form (no light carried by several surfaces), the surfaces that carry sphere lights are
+        // spheres, and the single rectangle light's surface IS the light's rectangle
+        bool unique = true, sphere_surfaces = true, same_rect = false;
+        for (int l = 0; l < scene.n_lights; ++l)
+        {
+            const int ls = scene.light_surface[l];
+            unique = unique && (scene.n_lights > 1 || ls != -2);
+            if (ls >= 0 && scene.bvh_nodes == nullptr)
+                sphere_surfaces = sphere_surfaces && scene.surf_shape[ls].kind == KYD_SHAPE_SPHERE;
+        }
+        if (all_rect && scene.n_lights == 1 && scene.light_surface[0] >= 0 && scene.bvh_nodes == nullptr)
+            same_rect = memcmp(&scene.surf_shape[scene.light_surface[0]], &scene.light_shape[0], sizeof(DevShape)) == 0;
+        traits = (all_rect && scene.n_lights == 1 && same_rect) ? TRAITS_AREA_RECTANGLE
+               : (all_sphere && unique && sphere_surfaces) ? TRAITS_AREA_SPHERE : TRAITS_ANY;
     }
 
     // persistent-style grids: enough blocks to fill every SM several times over, grid-stride inside
@@ -773,22 +923,48 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.direct_only = direct_only ? 1 : 0;
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
             wp.no_pending = nee ? 0 : 1;
+            wp.pair_kernel = plan.pair_kernel ? 1 : 0;
 
             // queue tails start at zero; the camera rays are generated inside the first intersect launch
             cudaMemsetAsync(counters->queue, 0, sizeof(counters->queue), stream);
             for (int bounce = 0; bounce <= last_bounce; ++bounce)
             {
-                T(StageTimer::INTERSECT);
-                if (bounce == 0)
-                    k_intersect<true><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
-                else
-                    k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
-                T(-1);
+                if (bounce == 0 || !plan.fused)
+                {
+                    T(StageTimer::INTERSECT);
+                    if (bounce == 0)
+                        k_intersect<true><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
+                    else
+                        k_intersect<false><<<grid256, 256, 0, stream>>>(wp, w, counters, bounce);
+                    T(-1);
+                    ++*launches;
+                }
+                if (plan.fused)   // the lobe queues the shade kernels of this bounce fill were consumed one bounce ago
+                    cudaMemsetAsync(&counters->queue[Q_LOBE0 + 4 * ((bounce & 1) ^ 1)], 0, 4 * sizeof(unsigned long long), stream);
                 T(StageTimer::SHADE);
-                launch_shade(traits, hot, plan.inline_queries, grid128, stream, wp, w, counters, bounce);
+                launch_shade(traits, hot, plan.inline_queries, plan.fused, grid128, stream, wp, w, counters, bounce);
                 T(-1);
-                *launches += 5;
-                if (nee)
+                *launches += 4;
+                if (plan.pair_kernel)
+                {
+                    // the light loop over (vertex, light) pairs, set-up and scene queries in one kernel per lobe
+                    T(StageTimer::LIGHT_SAMPLE);
+#if !KYD_BIG_SCENE
+                    if (traits == TRAITS_AREA_SPHERE)
+                    {
+                        k_nee<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                    }
+                    else
+#endif
+                    {
+                        k_nee<LOBE_LAMBERT, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee<LOBE_PHONG, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                    }
+                    T(-1);
+                    *launches += 2;
+                }
+                else if (nee)
                 {
                     if (wp.split_light_sample)
                     {

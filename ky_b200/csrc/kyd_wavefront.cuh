@@ -71,7 +71,10 @@ enum { FLAG_PREV_SPECULAR = 1, FLAG_SURFACE_SHIFT = 4, FLAG_SURFACE_MASK = 0xfff
 enum { PAIR_LIGHT_SHIFT = 24, PAIR_SLOT_MASK = (1 << 24) - 1 };
 // flags word of a light-sampling line (w of the light query's direction unit)
 // (bits 8..: 1 + the light's surface when the BSDF-sampled query is in its occlusion form, NeeRay::light_surface)
-enum { NEE_REF_BSDF = 1, NEE_REF_LIGHT = 2, NEE_BSDF_LIVE = 4, NEE_LIGHT_SURFACE_SHIFT = 8 };
+// (NEE_LIGHT_LIVE: the light-sampled query has to be traced.  Its tmax cannot say so: a light point closer than 2e-3 -- a
+// sphere light sampled from a point on its own surface -- gives a NEGATIVE tmax = distance - 2e-3 (ky.cpp:3193), which the
+// reference answers "not occluded")
+enum { NEE_REF_BSDF = 1, NEE_REF_LIGHT = 2, NEE_BSDF_LIVE = 4, NEE_LIGHT_LIVE = 8, NEE_LIGHT_SURFACE_SHIFT = 8 };
 
 struct WaveParams
 {
@@ -83,6 +86,9 @@ struct WaveParams
     int direct_only;          // direct_lighting_t: stop after the first vertex' light loop
     int split_light_sample;   // light-sample as its own kernel (KYD_FLAG_SPLIT_LIGHT_SAMPLE) instead of inside shade
     int no_pending;           // light queries are traced inside shade (one light, headline kernels): no path ever carries pending Ld
+    int pair_kernel;          // headline configuration with several lights: the light loop runs in k_nee, one thread per (vertex, light);
+                              // results are 16 bytes per pair at [slot * n_lights + light] of the light-sampling buffer, every light of
+                              // a vertex has one, and the vertex' beta is read from its vertex record
 };
 
 KYD_DEV float4* path_line(const WaveBuffers& w, int slot) { return w.path + (size_t)slot * PATH_UNITS; }
@@ -244,8 +250,22 @@ KYD_DEV void store_path_tail(float4* p, float3 beta, float3 Lo, unsigned long lo
 // Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576.  `pending` = the lights that
 // got a light-sampling line; the others' values are exactly +0 (no query of theirs could contribute) and adding +0 to
 // the running sum, which starts at +0 and therefore is never -0, changes nothing -- so they are skipped, in light order.
-KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsigned pending, float3 Lo)
+KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsigned pending, float3 Lo, bool pair_kernel = false)
 {
+    if (pending != 0 && pair_kernel)
+    {
+        // k_nee's results: every light of the vertex, in light order -- sample_all_light's own sum (ky.cpp:3864-3869)
+        const int n_lights = c_scene.n_lights;
+        const float4* res = w.nee + (size_t)slot * n_lights;
+        const float4 vb = vertex_line(w, slot)[V_BETA];
+        float3 Ld = KYD_BLACK;
+        for (int l = 0; l < n_lights; ++l)
+        {
+            const float4 e = res[l];
+            Ld = add(Ld, V3(e.x, e.y, e.z));
+        }
+        return add(Lo, cmulc(V3(vb.x, vb.y, vb.z), Ld));
+    }
     if (pending != 0)
     {
         const float4* line0 = nee_line(w, plane, __ffs(pending) - 1, slot);
@@ -295,7 +315,7 @@ __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(Wav
     const int* __restrict__ queue = parity ? w.queue_b : w.queue_a;
     unsigned long long* const tails[4] = { &counters->queue[Q_LOBE0 + 4 * parity], &counters->queue[Q_LOBE0 + 4 * parity + 1],
                                            &counters->queue[Q_LOBE0 + 4 * parity + 2], &counters->queue[Q_LOBE0 + 4 * parity + 3] };
-    int* const lobe_queues[4] = { w.queue_lobe[0], w.queue_lobe[1], w.queue_lobe[2], w.queue_lobe[3] };
+    int* const lobe_queues[4] = { w.queue_lobe[parity][0], w.queue_lobe[parity][1], w.queue_lobe[parity][2], w.queue_lobe[parity][3] };
     WarpPush<4> push;
     push.init();
     const bool has_env = c_scene.env_light >= 0;
@@ -374,7 +394,7 @@ __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(Wav
                 // Lo += beta * environment_lighting after a specular bounce
                 PathState st;
                 unpack_path(st, o, d, p[P_BETA], p[P_TAIL]);
-                float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
+                float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel != 0);
                 Lo = add(Lo, cmulc(st.beta, environment_lighting()));
                 store_path_ray(p, r.o, o.w, r.d, flags & FLAG_PREV_SPECULAR); // pending consumed
                 store_path_tail(p, st.beta, Lo, st.rng);
@@ -438,8 +458,8 @@ KYD_DEV void light_sample_pair(int ds, const HitGeom& g, const Bsdf& b, int l, S
 KYD_DEV void store_nee_line(float4* line, const NeeRay& qb, const NeeRay& ql, float3 vertex_beta)
 {
     const int flags = (qb.ref_query ? NEE_REF_BSDF : 0) | (ql.ref_query ? NEE_REF_LIGHT : 0) | (qb.active ? NEE_BSDF_LIVE : 0) |
-                      ((qb.light_surface + 1) << NEE_LIGHT_SURFACE_SHIFT);
-    line[N_LIGHT_O] = make_float4(ql.ray.o.x, ql.ray.o.y, ql.ray.o.z, ql.active ? ql.ray.tmax : -1.f); // tmax < 0: no query
+                      (ql.active ? NEE_LIGHT_LIVE : 0) | ((qb.light_surface + 1) << NEE_LIGHT_SURFACE_SHIFT);
+    line[N_LIGHT_O] = make_float4(ql.ray.o.x, ql.ray.o.y, ql.ray.o.z, ql.ray.tmax);
     line[N_LIGHT_D] = make_float4(ql.ray.d.x, ql.ray.d.y, ql.ray.d.z, __int_as_float(flags));
     line[N_LIGHT_VALUE] = make_float4(ql.value.x, ql.value.y, ql.value.z, vertex_beta.x);
     line[N_MIXED] = make_float4(vertex_beta.y, vertex_beta.z, qb.value.x, qb.value.y);
@@ -481,18 +501,40 @@ KYD_DEV float3 nee_resolve_pair(int ds, const NeeRay& qb, const NeeRay& ql, Shad
     return (ds == KYD_DS_BSDF || ds == KYD_DS_BSDF_MIS) ? Lb : Ll;
 }
 
+// what shading a vertex leaves behind: the path's state after it (shade_queue writes it back, and -- fused configuration --
+// first traces the next ray)
+struct VertexOut
+{
+    bool alive;                 // the path continues with the ray (o, d)
+    float3 o, d;
+    int flags;                  // FLAG_PREV_SPECULAR | pending lights of this vertex
+    float3 beta, Lo;
+    unsigned long long rng;
+    unsigned pairs;             // lights that got a light-sampling line (deferred queries)
+    bool split_vertex;          // a vertex record was written for the stand-alone light-sample stage
+    bool traced;                // the next ray's closest hit is already known (hit_surface, hit_t)
+    int hit_surface;
+    float hit_t;
+};
+
 // ---- shade: one path vertex (ky.cpp:4545-4613), specialised by lobe ---------------------------------------
 // HOT: the headline configuration (path_tracing_iteration_t, both_mis, LCG48 sampler, light-sample inside shade)
 // with those run-time switches compiled out; !HOT reads them from the parameters
 template <int LOBE, int TRAITS, bool HOT, int NL>
-KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, bool* out_alive, unsigned* out_pairs,
-                          bool* out_split_vertex, ShadeCounts* counts, float4 rec0, float4 rec1, float4 rec2, float4 rec3)
+KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, int bounce, int n_lights, VertexOut* out,
+                          ShadeCounts* counts, float4 rec0, float4 rec1, float4 rec2, float4 rec3)
 {
+    bool alive_flag = false, split_flag = false;
+    unsigned pairs_value = 0;
+    bool* out_alive = &alive_flag;
+    bool* out_split_vertex = &split_flag;
+    unsigned* out_pairs = &pairs_value;
     const int ds = HOT ? (int)KYD_DS_BOTH_MIS : wp.rp.direct_sample;
     const bool direct_only = HOT ? false : wp.direct_only != 0;
-    const bool split_light_sample = HOT ? false : wp.split_light_sample != 0;
+    // the light loop as a kernel of its own over (vertex, light) pairs: the measurement mode KYD_FLAG_SPLIT_LIGHT_SAMPLE, and
+    // -- always -- the headline configuration with several lights (k_nee)
+    const bool split_light_sample = HOT ? (NL == NL_MANY) : wp.split_light_sample != 0;
     const bool debug_sampler = HOT ? false : wp.rp.sampler == KYD_SAMPLER_DEBUG;
-    float4* p = path_line(w, slot);
     PathState st;
     unpack_path(st, rec0, rec1, rec2, rec3);
     Ray r;
@@ -503,7 +545,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     const int surface = st.surface();
 
     // light gathered at the previous vertex (see file header)
-    float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
+    float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel != 0);
     unsigned new_pending = 0;   // lights that get a light-sampling line at this vertex
 
     HitGeom g = shape_hit_geom(surface_shape(surface), r, st.t);
@@ -540,12 +582,13 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                 {
                     // vertex record for the light-sample stage
                     float4* v = vertex_line(w, slot);
-                    v[V_POSITION] = make_float4(g.position.x, g.position.y, g.position.z, 0.f);
+                    // (the spare words carry the shading frame's s and t axes: k_nee's five threads per vertex need not rebuild them)
+                    v[V_POSITION] = make_float4(g.position.x, g.position.y, g.position.z, b.f.s.x);
                     v[V_NORMAL] = make_float4(g.normal.x, g.normal.y, g.normal.z, b.exponent);
-                    v[V_WO] = make_float4(g.wo.x, g.wo.y, g.wo.z, 0.f);
-                    v[V_COLOR] = make_float4(b.a.x, b.a.y, b.a.z, 0.f);
-                    v[V_RNG] = make_float4(__uint_as_float((unsigned)smp.state), __uint_as_float((unsigned)(smp.state >> 32)), 0.f, 0.f);
-                    v[V_BETA] = make_float4(beta.x, beta.y, beta.z, 0.f);
+                    v[V_WO] = make_float4(g.wo.x, g.wo.y, g.wo.z, b.f.s.y);
+                    v[V_COLOR] = make_float4(b.a.x, b.a.y, b.a.z, b.f.s.z);
+                    v[V_RNG] = make_float4(__uint_as_float((unsigned)smp.state), __uint_as_float((unsigned)(smp.state >> 32)), b.f.t.x, b.f.t.y);
+                    v[V_BETA] = make_float4(beta.x, beta.y, beta.z, b.f.t.z);
                     new_pending = (1u << n_lights) - 1u;   // the light-sample kernel writes a line for every light
                     *out_split_vertex = true;
                 }
@@ -639,45 +682,215 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
             }
         }
     }
-    // both sectors go back whole; a path that ends here is read again only by k_accumulate, which needs Lo (sector 1)
-    // and -- only where light queries are deferred -- the pending count in sector 0
-    if (*out_alive || !wp.no_pending)
-        store_path_ray(p, next_o, KYD_INF, next_d, next_flags | (int)(new_pending << FLAG_PENDING_SHIFT));
-    store_path_tail(p, next_beta, Lo, rng_state);
+    out->alive = alive_flag;
+    out->o = next_o;
+    out->d = next_d;
+    out->flags = next_flags | (int)(new_pending << FLAG_PENDING_SHIFT);
+    out->beta = next_beta;
+    out->Lo = Lo;
+    out->rng = rng_state;
+    out->pairs = pairs_value;
+    out->split_vertex = split_flag;
+    out->traced = false;
+    out->hit_surface = -1;
+    out->hit_t = KYD_INF;
 }
 
-template <int LOBE, int TRAITS, bool HOT, int NL>
+// ---- shade of the headline kernels with one light (Lambert / Phong lobes): the same vertex as shade_vertex<.., HOT, NL_ONE>,
+// arranged for code size.  These kernels are instruction-fetch bound (a vertex is ~900 warp instructions of mostly
+// straight-line code against a 6 KB L0 / 32 KB L1.5 instruction cache; profiles/r02_ab_variants.txt), so what a vertex does more
+// than once runs through ONE copy of its code:
+//   - bsdf_t::sample: once for the light loop's BSDF-sampled query (ky.cpp:3977), once for the path's continuation (ky.cpp:4586);
+//   - the scene queries: the BSDF-sampled light query (in its occlusion form: the host selects the specialised traits only
+//     then), the light-sampled occlusion query and -- FUSE -- the closest hit of the path's next ray are all walks of
+//     scene_closest_2p from different starting states.
+// A three-trip loop: trip 0 = BSDF-sampled light query, trip 1 = light-sampled query (and L += beta * Ld), trip 2 = continuation.
+// The draws are the reference's: random_bsdf, random_light (ky.cpp:3866-3868, g++ order), then the continuation's pair.
+template <int LOBE, int TRAITS, bool FUSE>
+KYD_DEV void shade_vertex_hot_one(const WaveParams& wp, int bounce, VertexOut* out, ShadeCounts* counts,
+                                  float4 rec0, float4 rec1, float4 rec2, float4 rec3)
+{
+    constexpr bool OCC = TRAITS != TRAITS_ANY;
+    PathState st;
+    unpack_path(st, rec0, rec1, rec2, rec3);
+    Ray r;
+    r.o = st.o;
+    r.d = st.d;
+    r.tmax = KYD_INF;
+    const float3 beta = st.beta;
+    const int surface = st.surface();
+    float3 Lo = st.Lo;   // (no light is ever pending in this configuration)
+
+    HitGeom g = shape_hit_geom(surface_shape(surface), r, st.t);
+    if (bounce == 0 || (st.flags & FLAG_PREV_SPECULAR))
+        Lo = add(Lo, cmulc(beta, surface_emission(surface, g)));
+
+    out->alive = false;
+    out->o = st.o;
+    out->d = st.d;
+    out->flags = 0;
+    out->beta = beta;
+    out->rng = st.rng;
+    out->pairs = 0u;
+    out->split_vertex = false;
+    out->traced = false;
+    out->hit_surface = -1;
+    out->hit_t = KYD_INF;
+    if (bounce < wp.rp.max_depth)
+    {
+        const DevMaterial& m = c_scene.materials[surface_material(surface)];
+        Bsdf b;
+        b.f = frame_from_z(g.normal);
+        b.t = KYD_BLACK;
+        b.eta_t = 1.f;
+        b.exponent = 0.f;
+        b.lobe = LOBE;
+        if (LOBE == LOBE_LAMBERT) b.a = m.kind == KYD_MAT_PLASTIC ? m.plastic_lambert : m.diffuse;
+        else { b.a = m.plastic_phong; b.exponent = m.exponent; }
+
+        Sampler smp;
+        smp.debug = false;
+        smp.state = st.rng;
+        const float2 random_bsdf = smp.get_float2();
+        const float2 random_light = smp.get_float2();
+        const float2 random_next = smp.get_float2();
+        float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
+        bool any_active = false;
+#pragma unroll 1
+        for (int trip = 0; trip < 3; ++trip)
+        {
+            // the ray of this trip, the starting state of its walk, and what its answer is worth
+            NeeRay q;
+            q.active = false;
+            q.ref_query = false;
+            q.value = KYD_BLACK;
+            q.light = 0;
+            q.light_surface = -1;
+            q.ray.o = q.ray.d = V3(0.f, 0.f, 0.f);
+            q.ray.tmax = -1.f;
+            if (trip != 1)
+            {
+                const BsdfSample bs = bsdf_sample(b, g.wo, trip == 0 ? random_bsdf : random_next);
+                if (trip == 0)
+                    q = nee_bsdf_from_sample<TRAITS>(g, b, 0, bs, true);      // estimate_direct_lighting_by_bsdf_mis, ky.cpp:3968-4033
+                else if (!(is_black(bs.f) || bs.pdf == 0.f))
+                {
+                    // the path's next vertex (ky.cpp:4586-4613)
+                    float3 nb = cmulc(beta, cdiv(mul(bs.f, abs_dot(bs.wi, g.normal)), bs.pdf));
+                    bool alive = true;
+                    if (bounce > 3)
+                    {
+                        const float rr = max_std(0.05f, 1 - max_component(nb));
+                        if (smp.get_float() < rr)
+                            alive = false;
+                        else
+                            nb = mul(nb, 1 / (1 - rr));
+                    }
+                    if (alive)
+                    {
+                        q.ray = spawn_ray(g, bs.wi);
+                        out->alive = true;
+                        out->o = q.ray.o;
+                        out->d = q.ray.d;
+                        out->flags = (bs.type & BSDF_SPECULAR) ? FLAG_PREV_SPECULAR : 0;
+                        out->beta = nb;
+                        out->rng = smp.state;
+                        q.active = FUSE;   // (not fused: the intersect kernel of the next bounce traces it)
+                    }
+                }
+            }
+            else
+                q = nee_light_setup<TRAITS>(g, b, 0, random_light, true);     // estimate_direct_lighting_by_emitter_mis, ky.cpp:4035-4074
+            if (trip < 2)
+                counts->ref_rays += q.ref_query ? 1u : 0u;
+
+            if (q.active)
+            {
+                counts->traced++;
+                if (!OCC && trip == 0 && q.light_surface < 0)
+                {
+                    // closest-hit form (a light carried by several surfaces, or the environment light)
+                    float t;
+                    const int s = wf_closest(q.ray, &t);
+                    Lb = nee_bsdf_resolve(q, s, t);
+                    any_active = true;
+                }
+                else
+                {
+                    float t;
+                    const int s = wf_closest_from(q.ray, q.light_surface, &t);
+                    if (trip == 0) { any_active = true; if (s == q.light_surface) Lb = q.value; }
+                    else if (trip == 1) { any_active = true; if (s < 0) Ll = q.value; }
+                    else
+                    {
+                        counts->ref_rays++;
+                        out->traced = true;
+                        out->hit_surface = s;
+                        out->hit_t = t;
+                    }
+                }
+            }
+            if (trip == 1)
+            {
+                // sample_all_light's sum with its one light: 0.5 Lb + 0.5 Ll (ky.cpp:4083), then L += beta * Ld (ky.cpp:4575-4576)
+                // (beta * 0 is 0 only for finite beta: a non-finite throughput keeps the reference's NaN)
+                const bool finite_beta = isfinite(beta.x) && isfinite(beta.y) && isfinite(beta.z);
+                if (any_active || !finite_beta)
+                    Lo = add(Lo, cmulc(beta, add(KYD_BLACK, add(mul(Lb, 0.5f), mul(Ll, 0.5f)))));
+            }
+        }
+    }
+    out->Lo = Lo;
+}
+
+// FUSE (headline configuration with one light; wavefront_plan().fused): shade also traces the path's next ray -- closest hit,
+// lobe classification, the miss -- and pushes the path straight into the NEXT bounce's lobe queue, so only camera rays go
+// through k_intersect.  That kernel had become a pure gather / scatter of path records once the two-phase traversal made its
+// arithmetic cheap (long-scoreboard bound, 2 TB/s of 32-byte sectors; profiles/r02_*): fused, its 64 B per ray never move.
+template <int LOBE, int TRAITS, bool HOT, int NL, bool FUSE>
 KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
 {
-    if ((LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG) && HOT && NL == NL_ONE)
-        stage_rects();   // this kernel traces its vertices' light queries itself
+    constexpr bool HOT_ONE = HOT && NL == NL_ONE && (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG);
+    if (HOT_ONE || FUSE)
+        stage_rects();   // this kernel traces scene queries itself
     const int parity = bounce & 1;
     const int n = (int)counters->queue[Q_LOBE0 + 4 * parity + LOBE];
-    const int* __restrict__ queue = w.queue_lobe[LOBE];
+    const int* __restrict__ queue = w.queue_lobe[parity][LOBE];
     int* __restrict__ next_queue = parity ? w.queue_a : w.queue_b;
     const int stride = gridDim.x * blockDim.x;
     const int n_lights = c_scene.n_lights;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    // queue 0: the next bounce's rays; queue 1: vertices for the stand-alone light-sample stage (split mode only);
+    // not fused -- queue 0: the next bounce's rays; queue 1: vertices for the stand-alone light-sample stage (split mode only);
     // pair queue: (vertex, light) pairs whose light-sampling line the shadow stage resolves
     unsigned long long* const tails[2] = { &counters->queue[Q_RAY0 + (parity ^ 1)], &counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)] };
     int* const out_queues[2] = { next_queue, w.queue_nee[LOBE == LOBE_PHONG] };
+    // fused: the next bounce's lobe queues
+    unsigned long long* const lobe_tails[4] = { &counters->queue[Q_LOBE0 + 4 * (parity ^ 1)], &counters->queue[Q_LOBE0 + 4 * (parity ^ 1) + 1],
+                                                &counters->queue[Q_LOBE0 + 4 * (parity ^ 1) + 2], &counters->queue[Q_LOBE0 + 4 * (parity ^ 1) + 3] };
+    int* const lobe_queues[4] = { w.queue_lobe[parity ^ 1][0], w.queue_lobe[parity ^ 1][1], w.queue_lobe[parity ^ 1][2], w.queue_lobe[parity ^ 1][3] };
     unsigned long long* const pair_tail = &counters->queue[Q_PAIR0 + (LOBE == LOBE_PHONG)];
     int* const pair_queue = w.queue_pair[LOBE == LOBE_PHONG];
-    constexpr bool DEFERS = !(HOT && NL == NL_ONE) && (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG);
+    // (vertex, light) pairs for the shadow stage: the general kernels only (headline kernels trace one light's queries
+    // themselves and hand several lights' to k_nee as whole vertices)
+    constexpr bool DEFERS = !HOT && (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG);
     WarpPush<2> push;
     push.init();
+    WarpPush<4> lobe_push;
+    lobe_push.init();
     PairPush pairs;
     pairs.init();
     ShadeCounts counts = { 0u, 0u };
+    const bool has_env = c_scene.env_light >= 0;
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&counters->shade_vertices, (unsigned long long)n); // traffic model of bench.py
 
     // whole warps iterate together so that the ballots of the push are convergent; the queue entry is read one
     // iteration ahead
-    // the single-light kernels have the registers to load the next vertex' record while this one is shaded (its queue
-    // entry is then read two iterations ahead); the others would spill (profiles/r01_ab_variants.txt)
-    constexpr bool PREFETCH = HOT && NL == NL_ONE;
+    // (KYD_SHADE_PREFETCH: the single-light kernels may also load the next vertex' record while this one is shaded)
+#ifndef KYD_SHADE_PREFETCH
+#define KYD_SHADE_PREFETCH 0   // (1: +16 registers for the next record, spills in the one-light kernels; A/B in profiles/r02_ab_variants.txt)
+#endif
+    constexpr bool PREFETCH = HOT && NL == NL_ONE && KYD_SHADE_PREFETCH != 0;
     long long ia = i;
     int slot_cur = ia < n ? queue[ia] : -1;
     int slot_next = ia + stride < n ? queue[ia + stride] : -1;
@@ -699,18 +912,67 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
         }
         bool alive = false, split_vertex = false;
         unsigned pair_mask = 0;
+        int next_lobe = -1;
         const int slot = slot_cur < 0 ? 0 : slot_cur;
         if (slot_cur >= 0)
         {
+            float4* p = path_line(w, slot);
             if (!PREFETCH)
             {
-                const float4* p0 = path_line(w, slot);
-                rec0 = p0[P_ORIGIN]; rec1 = p0[P_DIRECTION]; rec2 = p0[P_BETA]; rec3 = p0[P_TAIL];
+                rec0 = p[P_ORIGIN]; rec1 = p[P_DIRECTION]; rec2 = p[P_BETA]; rec3 = p[P_TAIL];
             }
-            shade_vertex<LOBE, TRAITS, HOT, NL>(wp, w, slot, bounce, n_lights, &alive, &pair_mask, &split_vertex, &counts, rec0, rec1, rec2, rec3);
+            VertexOut v;
+            if (HOT_ONE)
+                shade_vertex_hot_one<LOBE, TRAITS, FUSE>(wp, bounce, &v, &counts, rec0, rec1, rec2, rec3);
+            else
+                shade_vertex<LOBE, TRAITS, HOT, NL>(wp, w, slot, bounce, n_lights, &v, &counts, rec0, rec1, rec2, rec3);
+            pair_mask = v.pairs;
+            split_vertex = v.split_vertex;
+            float hit_t = KYD_INF;
+            if (FUSE && v.alive)
+            {
+                // scene_t::intersect for the next loop iteration of path_tracing_iteration_t::Li (ky.cpp:4542)
+                if (!v.traced)
+                {
+                    Ray nr;
+                    nr.o = v.o; nr.d = v.d; nr.tmax = KYD_INF;
+                    v.hit_surface = wf_closest(nr, &v.hit_t);
+                    counts.ref_rays++;
+                    counts.traced++;
+                }
+                if (v.hit_surface >= 0)
+                {
+                    Ray nr;
+                    nr.o = v.o; nr.d = v.d; nr.tmax = KYD_INF;
+                    next_lobe = classify_lobe(v.hit_surface, nr, v.hit_t);
+                    v.flags |= (v.hit_surface + 1) << FLAG_SURFACE_SHIFT;
+                    hit_t = v.hit_t;
+                }
+                else
+                {
+                    // the path leaves the scene: Lo += beta * environment_lighting after a specular bounce (ky.cpp:4548-4563)
+                    if (has_env && (v.flags & FLAG_PREV_SPECULAR))
+                        v.Lo = add(v.Lo, cmulc(v.beta, environment_lighting()));
+                    v.alive = false;
+                }
+            }
+            alive = v.alive;
+            // both sectors go back whole; a path that ends here is read again only by k_accumulate, which needs Lo (sector 1)
+            // and -- only where light queries are deferred -- the pending count in sector 0
+            if (v.alive || !wp.no_pending)
+                store_path_ray(p, v.o, hit_t, v.d, v.flags);
+            store_path_tail(p, v.beta, v.Lo, v.rng);
         }
-        push.commit(out_queues);
-        push.reserve((alive ? 1u : 0u) | (split_vertex ? 2u : 0u), slot, tails);
+        if (FUSE)
+        {
+            lobe_push.commit(lobe_queues);
+            lobe_push.reserve(next_lobe >= 0 ? (1u << next_lobe) : 0u, slot, lobe_tails);
+        }
+        else
+        {
+            push.commit(out_queues);
+            push.reserve((alive ? 1u : 0u) | (split_vertex ? 2u : 0u), slot, tails);
+        }
         if (DEFERS)
         {
             pairs.commit(pair_queue);
@@ -725,7 +987,10 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
         else
             slot_cur = slot_ahead;
     }
-    push.commit(out_queues);
+    if (FUSE)
+        lobe_push.commit(lobe_queues);
+    else
+        push.commit(out_queues);
     if (DEFERS)
         pairs.commit(pair_queue);
     flush_counters(counts.ref_rays, counts.traced, counters);
@@ -733,10 +998,10 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
 
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
 // shades most vertices, does not pay for Phong's pow() or the dielectric's Fresnel terms)
-template <int LOBE, int TRAITS, bool HOT, int NL>
+template <int LOBE, int TRAITS, bool HOT, int NL, bool FUSE>
 __global__ void __launch_bounds__(SHADE_THREADS, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
-    shade_queue<LOBE, TRAITS, HOT, NL>(wp, w, counters, bounce);
+    shade_queue<LOBE, TRAITS, HOT, NL, FUSE>(wp, w, counters, bounce);
 }
 
 // ---- light-sample as its own stage (KYD_FLAG_SPLIT_LIGHT_SAMPLE): one thread per (vertex, light) -------------
@@ -780,6 +1045,94 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 {
     light_sample_queue<LOBE_LAMBERT>(wp, w, counters);
     light_sample_queue<LOBE_PHONG>(wp, w, counters);
+}
+
+// ---- k_nee: the light loop of the headline configuration with several lights, one thread per (vertex, light) -----------
+// sample_all_light (ky.cpp:3834-3872) spends ~450 instructions per light on the two estimators' set-up (a BSDF sample, a
+// cone sample of the sphere light, two BSDF evaluations, their pdfs) before any ray is traced; with Veach's five lights
+// that loop was 80 % of a shade thread's work, serial, at 124 registers.  Here every (vertex, light) pair is a thread: the
+// pairs of a vertex sit in adjacent lanes, so its 96-byte vertex record (written by shade) is one broadcast load, the set-up
+// of all lights runs in parallel, and the two scene queries are traced on the spot through one copy of the closest-hit
+// walk -- no light-sampling lines, no shadow stage.  The estimator value of the pair (0.5 Lb + 0.5 Ll, ky.cpp:4083) goes to
+// results[slot * n_lights + light]; the path adds its vertex' values in light order at its next stage (add_pending).
+#ifndef KYD_NEE_CULL
+#define KYD_NEE_CULL 1
+#endif
+#ifndef KYD_NEE_MIN_BLOCKS
+#define KYD_NEE_MIN_BLOCKS 4
+#endif
+template <int LOBE, int TRAITS>
+__global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
+{
+    stage_rects();
+    const int n = (int)counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)];
+    const int* __restrict__ queue = w.queue_nee[LOBE == LOBE_PHONG];
+    const int n_lights = c_scene.n_lights;
+    const long long total = (long long)n * n_lights;
+    const int stride = gridDim.x * blockDim.x;
+    unsigned rays = 0, traced = 0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride)
+    {
+        const int vertex = (int)(idx / n_lights);        // vertex-major: the lights of a vertex are adjacent lanes
+        const int l = (int)(idx - (long long)vertex * n_lights);
+        const int slot = queue[vertex];
+        const float4* v = vertex_line(w, slot);
+        const float4 p4 = v[V_POSITION], n4 = v[V_NORMAL], wo4 = v[V_WO], c4 = v[V_COLOR], rng4 = v[V_RNG], vb = v[V_BETA];
+        HitGeom g;
+        g.position = V3(p4.x, p4.y, p4.z);
+        g.normal = V3(n4.x, n4.y, n4.z);
+        g.wo = V3(wo4.x, wo4.y, wo4.z);
+        Bsdf b;
+        b.f.s = V3(p4.w, wo4.w, c4.w);
+        b.f.t = V3(rng4.z, rng4.w, vb.w);
+        b.f.n = normalize(g.normal);                     // frame_t's z axis (ky.cpp:537-541)
+        b.a = V3(c4.x, c4.y, c4.z);
+        b.t = KYD_BLACK;
+        b.eta_t = 1.f;
+        b.exponent = n4.w;
+        b.lobe = LOBE;
+
+        Sampler smp;
+        smp.debug = false;
+        smp.state = (unsigned long long)__float_as_uint(rng4.x) | ((unsigned long long)__float_as_uint(rng4.y) << 32);
+        smp.skip(4 * l);                                 // both_mis: four draws per light (ky.cpp:3866-3868)
+        const float2 random_bsdf = smp.get_float2();
+        const float2 random_light = smp.get_float2();
+        float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
+#pragma unroll 1
+        for (int trip = 0; trip < 2; ++trip)
+        {
+            NeeRay q;
+            if (trip == 0) q = nee_bsdf_setup<TRAITS, KYD_NEE_CULL != 0>(g, b, l, random_bsdf, true);   // ky.cpp:3968-4033
+            else q = nee_light_setup<TRAITS>(g, b, l, random_light, true);             // ky.cpp:4035-4074
+            rays += q.ref_query ? 1u : 0u;
+            if (q.active)
+            {
+                traced++;
+                float3 value;
+                if (trip == 0 && q.light_surface < 0)
+                {
+                    // closest-hit form (a light carried by several surfaces, or the environment light)
+                    float t;
+                    const int s = wf_closest(q.ray, &t);
+                    value = nee_bsdf_resolve(q, s, t);
+                }
+                else
+                {
+                    float t;
+                    const int s = wf_closest_from(q.ray, q.light_surface, &t);
+                    value = (trip == 0 ? s == q.light_surface : s < 0) ? q.value : KYD_BLACK;
+                }
+                if (trip == 0) Lb = value;
+                else Ll = value;
+            }
+        }
+        const float3 e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
+        w.nee[(size_t)slot * n_lights + l] = make_float4(e.x, e.y, e.z, 0.f);
+    }
+    flush_counters(rays, traced, counters);
+    if (LOBE == LOBE_LAMBERT && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&counters->shade_lines, (unsigned long long)total);
 }
 
 // ---- shadow: the scene queries of the light loop and the estimators' second halves ------------------------
@@ -871,12 +1224,13 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
                     traced++;
             }
             {
+                const bool light_live = (flags & NEE_LIGHT_LIVE) != 0;
                 Ray r;
                 r.o = V3(lo.x, lo.y, lo.z);
                 r.d = V3(ld.x, ld.y, ld.z);
-                r.tmax = lo.w;                    // < 0: no query, nothing can be hit
+                r.tmax = light_live ? lo.w : -1.f;   // (no query: nothing can be hit)
                 const bool occluded = wf_any_hit(r);
-                if (lo.w >= 0.f)
+                if (light_live)
                 {
                     Ll = occluded ? KYD_BLACK : V3(lv.x, lv.y, lv.z);
                     traced++;
@@ -921,7 +1275,7 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveParams wp, WaveBuffers w
             {
                 PathState st;
                 unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
-                Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo);
+                Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel != 0);
             }
             L = add(L, mul(Li, wp.rp.weight));
         }

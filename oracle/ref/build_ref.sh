@@ -8,6 +8,8 @@
 #   oracle/_ref/libky_ref_det.so        + P5 (stateless plastic lobe draw) + crlibm_shim.c
 #   oracle/_ref/libky_ref_glibc.so      + P5, glibc's own float libm (no crlibm_shim): what the libm contract costs,
 #                                       measured by tests/test_libm_contract.py
+#   oracle/_ref/ky_ref_entries          the reference's own render_* entry points and main(), verbatim, compiled against
+#                                       include/ky.hpp and linked with libkyd.so (the drop-in proof; needs libkyd.so built)
 #   oracle/_ref/libsmallpt_kernel_ref.so       smallpt2pbrt/smallpt_kernel.cpp, CPU_RENDER configuration
 #   oracle/_ref/libsmallpt_kernel_cuda_ref.so  the same file as smallpt_kernel.cu compiles it (USE_CUDA): the reference's
 #                                       own CUDA kernel, built for sm_100a (timed beside kyd_render_smallpt_f64)
@@ -82,6 +84,16 @@ if command -v nvcc >/dev/null 2>&1; then
     patch1 S1 '/^int main(int argc, char\* argv\[\])/,$d' '^int main(int argc, char\* argv\[\])'
     nvcc -std=c++20 -O3 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -w -I"$out" -shared "$here/smallpt_cuda_addon.cu" \
         -o "$out/libsmallpt_kernel_cuda_ref.so"
+fi
+
+# ---- the drop-in proof: the reference's own entry points + main(), verbatim, against include/ky.hpp + libkyd.so ----
+kyd_lib="$here/../../ky_b200/lib"
+if [ -f "$kyd_lib/libkyd.so" ]; then
+    n=$(grep -c '^void render_single_scene(int argc, char\* argv\[\])' "$ref/ky.cpp" || true)
+    if [ "$n" != "1" ]; then echo "build_ref: entry-point anchor matched $n lines" >&2; exit 1; fi
+    sed -n '/^void render_single_scene(int argc, char\* argv\[\])/,$p' "$ref/ky.cpp" > "$out/ref_entries.inc"
+    g++ -std=c++20 -O1 -ffp-contract=off -w -I"$here/../../include" -I"$out" "$here/ref_entries_main.cpp" -o "$out/ky_ref_entries" \
+        -L"$kyd_lib" -lkyd -Wl,-rpath,'$ORIGIN/../../ky_b200/lib'
 fi
 
 echo "build_ref: built $(ls "$out"/*.so | tr '\n' ' ')"

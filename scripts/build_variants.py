@@ -8,6 +8,19 @@ variants = {
     "imb3": ["-DKYD_INTERSECT_MIN_BLOCKS=3"],
     "imb4": ["-DKYD_INTERSECT_MIN_BLOCKS=4"],
     "onephase": ["-DKYD_TWO_PHASE=0"],
+    "unroll4": ["-DKYD_TRAVERSAL_UNROLL=4"],
+    "nocull": ["-DKYD_NEE_CULL=0"],
+    "nee5": ["-DKYD_NEE_MIN_BLOCKS=5"],
+    "nee6": ["-DKYD_NEE_MIN_BLOCKS=6"],
+    "nee8": ["-DKYD_NEE_MIN_BLOCKS=8"],
+    "nopf": ["-DKYD_SHADE_PREFETCH=0"],
+    "nopf_mb5": ["-DKYD_SHADE_PREFETCH=0", "-DKYD_SHADE_MIN_BLOCKS=5"],
+    "nopf_mb6": ["-DKYD_SHADE_PREFETCH=0", "-DKYD_SHADE_MIN_BLOCKS=6"],
+    "mb3": ["-DKYD_SHADE_MIN_BLOCKS=3"],
+    "u1_mb6": ["-DKYD_SHADE_MIN_BLOCKS=6"],
+    "u1_mb5": ["-DKYD_SHADE_MIN_BLOCKS=5"],
+    "noinline": ["-DKYD_WF_NOINLINE=1"],
+    "noinline_mb6": ["-DKYD_WF_NOINLINE=1", "-DKYD_SHADE_MIN_BLOCKS=6"],
     "imb2": ["-DKYD_INTERSECT_MIN_BLOCKS=2"],
     "mb5": ["-DKYD_SHADE_MIN_BLOCKS=5"],
     "mb6": ["-DKYD_SHADE_MIN_BLOCKS=6"],

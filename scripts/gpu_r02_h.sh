@@ -1,0 +1,13 @@
+# round 2, session H: full GPU suite + bench (fused default) + profiles (C5 and C3)
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r02h_gpu_tests.log 2>&1; tail -4 gpurun_out/r02h_gpu_tests.log; grep -E "^(FAILED|ERROR)" gpurun_out/r02h_gpu_tests.log | head -20
+timeout 900 python bench.py > gpurun_out/r02h_bench.json 2> gpurun_out/r02h_bench.err; tail -3 gpurun_out/r02h_bench.err
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02h_bench.json"))
+print("C5", round(d["value"]), {k: round(v, 1) for k, v in d["stage_ms_per_step"].items()}, "e2e", round(d["e2e"]["value"]), "cpu", d.get("cpu_baseline", {}).get("value"))
+for c, v in d.get("configs", {}).items():
+    print("   ", c, round(v["msamples_per_s"], 1), {k: round(x, 1) for k, x in v["stage_ms_rank0"].items()})
+PY
+bash scripts/gpu_prof.sh r02h C3 > /dev/null 2>&1
+ls -la gpurun_out/r02h_*

@@ -108,8 +108,24 @@ def to_json(path, out_path, workload):
     print(json.dumps(doc, indent=1))
 
 
+def stalls(path):
+    """warp-stall reasons per issued instruction, per captured launch"""
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    idx = {h: i for i, h in enumerate(hdr)}
+    keys = [h for h in hdr if "issue_stalled" in h and h.endswith("_per_issue_active.ratio") and "not_issued" not in h]
+    for r in rows[2:]:
+        vals = sorted(((float(r[idx[k]].replace(",", "")) if r[idx[k]] else 0.0,
+                        k.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for k in keys), reverse=True)[:8]
+        print(f"--- {r[idx['ID']]} {short(r[idx['Kernel Name']])}")
+        print("    " + ", ".join(f"{k} {v:.2f}" for v, k in vals))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "stalls":
+        stalls(sys.argv[2])
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2])
     elif sys.argv[1] == "json":
         to_json(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "bench.py --steps 1 --warmup 1 --spp-per-step 2")

@@ -210,3 +210,31 @@ def big_scene(extra=360, seed=3):
         shapes = shapes + [ky.describe_shape(kind, params)]
         surfaces = surfaces + [sf]
     return CustomScene(base, shapes, materials, lights, surfaces, base.desc.environment_light)
+
+
+def inside_sphere_light_scene(only_light=False):
+    """Cornell box inside a sphere area light of radius 6 around the origin (the camera sits inside it too): every shading
+    point takes the inside branch of sphere_t::sample_direction -- area sampling with the SHADING point's normal in the
+    pdf (ky.cpp:1422-1444, a reference quirk) -- and of sphere_t::pdf_direction, which falls through to the generic
+    re-intersection (ky.cpp:1503-1513, 1055-1090).  No reference scene reaches them.  only_light: the sphere is the scene's
+    single light (the specialised single-sphere-light kernels); else it is a second light next to the ceiling rectangle."""
+    import ky_b200 as ky
+    base = make_scene("cornell")
+    shapes, materials, lights, surfaces = base.shapes, base.materials, base.lights, base.surfaces
+    ball = ky.describe_shape(ky.SHAPE_SPHERE, [0.0, 0.0, 0.0, 6.0])
+    glow = ky.Light()
+    glow.kind = ky.LIGHT_AREA
+    glow.color[:] = [0.35, 0.3, 0.25]
+    glow.shape = len(shapes)
+    shell = ky.Surface()
+    shell.shape, shell.material = len(shapes), surfaces[2].material
+    if only_light:
+        kept = []
+        for sf in surfaces:
+            c = ky.Surface()
+            c.shape, c.material, c.area_light = sf.shape, sf.material, -1
+            kept.append(c)
+        shell.area_light = 0
+        return CustomScene(base, shapes + [ball], materials, [glow], kept + [shell], -1)
+    shell.area_light = len(lights)
+    return CustomScene(base, shapes + [ball], materials, lights + [glow], surfaces + [shell], base.desc.environment_light)

@@ -11,9 +11,15 @@ pytestmark = pytest.mark.gpu
 TRAVERSAL = 2
 
 
-@pytest.mark.parametrize("scene_key", ["cornell", "cornell_large_mirror_all_lights", "veach", "smallpt", "shapes", "ties_first", "ties_last"])
+@pytest.mark.parametrize("scene_key", ["cornell", "cornell_large_mirror_all_lights", "veach", "smallpt", "shapes", "ties_first", "ties_last",
+                                       "inside_sphere_light", "inside_sphere_light_only"])
 def test_two_phase_traversal_equals_the_list_walk(device, scene_key):
-    scene = cases.coplanar_tie_scene(scene_key[5:]) if scene_key.startswith("ties_") else cases.make_scene(scene_key)
+    if scene_key.startswith("ties_"):
+        scene = cases.coplanar_tie_scene(scene_key[5:])
+    elif scene_key.startswith("inside_sphere_light"):
+        scene = cases.inside_sphere_light_scene(scene_key.endswith("_only"))   # ray origins far outside the rectangles' bounds
+    else:
+        scene = cases.make_scene(scene_key)
     device.upload(scene)
     for first in (0, 1 << 40):
         bad, hits = device.selftest(TRAVERSAL, first, 1 << 24)
