@@ -510,6 +510,34 @@ def main():
                                         "intersect_kernel_frac": (cj.flops_intersect / (cj.stage_ms[1] * 1e-3) / peak_lane_ops) if cj.stage_ms[1] > 0 else None},
                 "vs_north_star_625_msamples_per_gpu": n_samples / ms / 1e3 / world / 625.0,
             }
+            if name == "C1" and world == 1:
+                # the reference's OWN CUDA kernel for this scene (smallpt2pbrt/smallpt_kernel.cu: FP64, recursive, no light
+                # sampling, one thread per pixel; built for sm_100a by oracle/ref/build_ref.sh) beside this library's FP64
+                # validation mode of the same algorithm -- a different algorithm from the FP32 both_mis path above, reported
+                # as the reference's GPU datum
+                ref_gpu = {"workload": "smallpt_kernel.cu Device::Render(1024, 768, 64 spp), FP64, wall clock incl. managed film allocation; child process"}
+                try:
+                    script = os.path.join(ROOT, "scripts", "ref_cuda_smallpt.py")
+                    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libsmallpt_kernel_cuda_ref.so")):
+                        for stack in (0, 8192):   # as written (default stack x 3), then with a larger base stack limit
+                            r = subprocess.run([sys.executable, script, "1024", "768", "64", str(stack)], capture_output=True, text=True, timeout=300)
+                            key = "as_written" if stack == 0 else "with_base_stack_8192"
+                            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+                            if r.returncode == 0 and lines:
+                                ref_gpu[key] = json.loads(lines[-1])
+                            else:
+                                ref_gpu[key] = {"failed": f"exit code {r.returncode}", "message": (r.stderr or r.stdout).strip()[-200:]}
+                        dev.render_smallpt_f64(256, 192, 4)
+                        t0 = time.perf_counter()
+                        dev.render_smallpt_f64(1024, 768, 64)
+                        ours_s = time.perf_counter() - t0
+                        ref_gpu["kyd_render_smallpt_f64_msamples_per_s"] = 1024 * 768 * 64 / ours_s / 1e6
+                        ref_gpu["kyd_render_smallpt_f64_kernel_msamples_per_s"] = 1024 * 768 * 64 / dev.stats().device_ms / 1e3
+                    else:
+                        ref_gpu["unavailable"] = "oracle/_ref/libsmallpt_kernel_cuda_ref.so not built"
+                except Exception as e:  # noqa: BLE001  (a measurement beside the contract: never fatal)
+                    ref_gpu["unavailable"] = repr(e)
+                configs[name]["reference_gpu"] = ref_gpu
             del cj
 
     if rank == 0:

@@ -99,7 +99,12 @@ KYD_MATH float cr_pow_reference(float x, float y) { return __double2float_rn(pow
 // 30 / 90 / 5000 are integers) -- is (-1)^y |x|^y, exactly and with symmetric rounding, so it takes the same path.
 // Everything else -- zero, non-finite or huge arguments, denormal results, values too close to a rounding
 // boundary (2^-15 of calls) -- evaluates the definition.  tests: kyd_selftest(KYD_SELFTEST_POW).
+#if defined(KYD_POW_INLINE) && KYD_POW_INLINE
 KYD_DEV float cr_pow(float x, float y)
+#else
+// (out of line: the Phong kernels call it at three sites, ~150 instructions each, and are instruction-fetch bound)
+__device__ __noinline__ float cr_pow(float x, float y)
+#endif
 {
 #if !defined(KYD_FAST_POW) || KYD_FAST_POW
     float ax = x;
@@ -1830,7 +1835,34 @@ KYD_DEV float3 nee_bsdf_trace(const NeeRay& q)
 
 // light-sampled half: estimate_direct_lighting_by_emitter (ky.cpp:3933-3962) when mis == false,
 // estimate_direct_lighting_by_emitter_mis (ky.cpp:4035-4074) when mis == true
-template <int TRAITS = TRAITS_ANY>
+// Conservative early-out of a light-sampled query of a PHONG lobe against a sphere light seen from outside (Veach: exponent
+// 5000).  The estimator multiplies by f = rho pow(wr . wi, n) (ky.cpp:2496-2499; the base is not clamped, so an even n also
+// lights the lobe around -wr); every direction into the light's cone makes an angle of at most asin(R / dist) with the axis
+// to its centre, hence |wr . wi| <= |wr . axis| + 2 R / dist.  If that bound stays below 2^(-170 / n) the power underflows to
+// exactly 0 (cr_pow returns 0 below 2^-160), f cos is black and the query contributes nothing -- without sampling the cone.
+// The reference's own shadow ray is still counted (it traces before it evaluates the BSDF, ky.cpp:4047-4052): the sample's
+// radiance is the light's (interior of the cone, u.x < 0.99: the sampled point faces the shading point) and its pdf positive.
+template <int TRAITS>
+KYD_DEV bool light_query_certainly_black(const HitGeom& g, const Bsdf& b, int light_index, float2 u)
+{
+    if (TRAITS != TRAITS_AREA_SPHERE || b.lobe != LOBE_PHONG)
+        return false;
+    if (is_black(c_scene.lights[light_index].color) || !(b.exponent >= 1.f) || !(u.x < 0.99f))
+        return false;
+    const DevShape& sphere = c_scene.light_shape[light_index];
+    const float3 pc = sub(sphere.p0, g.position);
+    const float d2 = msq(pc);
+    if (!(d2 > 1.02f * sphere.radius * sphere.radius) || !(d2 < 1e30f))
+        return false;
+    const float inv = rsqrtf(d2);
+    const float spread = 2.f * sphere.radius * inv;
+    const float3 wr = sub(mul(b.f.n, 2.f * dot(b.f.n, g.wo)), g.wo);     // mirror direction of wo about the shading normal
+    const float ca = dot(wr, pc) * inv * rsqrtf(fmaxf(msq(wr), 1e-30f));
+    const float limit = exp2f(__fdividef(-170.f, b.exponent)) - 0.01f;
+    return (ca + spread < limit) && (ca - spread > -limit);
+}
+
+template <int TRAITS = TRAITS_ANY, bool CULL = false>
 KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index, float2 random_light, bool mis)
 {
     NeeRay q;
@@ -1842,6 +1874,11 @@ KYD_DEV NeeRay nee_light_setup(const HitGeom& g, const Bsdf& b, int light_index,
     const DevLight& l = c_scene.lights[light_index];
     if (bsdf_is_delta(b.lobe))
         return q;
+    if (CULL && light_query_certainly_black<TRAITS>(g, b, light_index, random_light))
+    {
+        q.ref_query = true;
+        return q;
+    }
     LightSample ls = light_sample_Li<TRAITS>(light_index, g, random_light);
     if (is_black(ls.Li) || (mis ? (ls.pdf <= 0) : (ls.pdf == 0)))
         return q;

@@ -297,7 +297,7 @@ KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 // ky.cpp:3714-3715, 1884-1892) instead of being written by a raygen kernel and read back; both sectors of the record
 // are written once, with the hit.  The host zeroes the queue tails before this launch.
 #ifndef KYD_INTERSECT_MIN_BLOCKS
-#define KYD_INTERSECT_MIN_BLOCKS 1
+#define KYD_INTERSECT_MIN_BLOCKS 3   // (80 registers: 24 warps per SM; left to itself the compiler takes 144 and one block per SM)
 #endif
 template <bool CAMERA>
 __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
@@ -887,10 +887,15 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     // whole warps iterate together so that the ballots of the push are convergent; the queue entry is read one
     // iteration ahead
     // (KYD_SHADE_PREFETCH: the single-light kernels may also load the next vertex' record while this one is shaded)
+#ifndef KYD_SHADE_PREFETCH_MANY
+#define KYD_SHADE_PREFETCH_MANY 1
+#endif
 #ifndef KYD_SHADE_PREFETCH
 #define KYD_SHADE_PREFETCH 0   // (1: +16 registers for the next record, spills in the one-light kernels; A/B in profiles/r02_ab_variants.txt)
 #endif
-    constexpr bool PREFETCH = HOT && NL == NL_ONE && KYD_SHADE_PREFETCH != 0;
+    // (the multi-light headline kernels hand their light loop to k_nee: what is left is short and waits for its record --
+    // long-scoreboard stalls 14 per issue in profiles/r02_c3_*; they have the registers to load the next one early)
+    constexpr bool PREFETCH = HOT && ((NL == NL_ONE && KYD_SHADE_PREFETCH != 0) || (NL == NL_MANY && KYD_SHADE_PREFETCH_MANY != 0));
     long long ia = i;
     int slot_cur = ia < n ? queue[ia] : -1;
     int slot_next = ia + stride < n ? queue[ia + stride] : -1;
@@ -1058,8 +1063,11 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 #ifndef KYD_NEE_CULL
 #define KYD_NEE_CULL 1
 #endif
+#ifndef KYD_NEE_PREFETCH
+#define KYD_NEE_PREFETCH 0   // (L2 prefetch of the next vertex record: 703 vs 747 Msamples/s on C3 -- the records are already L1/L2 hits, the extra requests only compete)
+#endif
 #ifndef KYD_NEE_MIN_BLOCKS
-#define KYD_NEE_MIN_BLOCKS 4
+#define KYD_NEE_MIN_BLOCKS 5   // 94 registers, 20 warps per SM (A/B in profiles/r02_ab_variants.txt: 4 -> 705, 5 -> 747, 6 -> 716, 8 -> 696 Msamples/s on C3)
 #endif
 template <int LOBE, int TRAITS>
 __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
@@ -1077,6 +1085,15 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
         const int l = (int)(idx - (long long)vertex * n_lights);
         const int slot = queue[vertex];
         const float4* v = vertex_line(w, slot);
+#if KYD_NEE_PREFETCH
+        if (idx + stride < total)
+        {
+            // the next iteration's vertex record on its way into L2 while this pair is worked on (no registers held)
+            const float4* vn = vertex_line(w, queue[(int)((idx + stride) / n_lights)]);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vn));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vn + 4));
+        }
+#endif
         const float4 p4 = v[V_POSITION], n4 = v[V_NORMAL], wo4 = v[V_WO], c4 = v[V_COLOR], rng4 = v[V_RNG], vb = v[V_BETA];
         HitGeom g;
         g.position = V3(p4.x, p4.y, p4.z);
@@ -1104,7 +1121,7 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
         {
             NeeRay q;
             if (trip == 0) q = nee_bsdf_setup<TRAITS, KYD_NEE_CULL != 0>(g, b, l, random_bsdf, true);   // ky.cpp:3968-4033
-            else q = nee_light_setup<TRAITS>(g, b, l, random_light, true);             // ky.cpp:4035-4074
+            else q = nee_light_setup<TRAITS, KYD_NEE_CULL != 0>(g, b, l, random_light, true);           // ky.cpp:4035-4074
             rays += q.ref_query ? 1u : 0u;
             if (q.active)
             {

@@ -13,8 +13,13 @@ extern "C" {
 // Runs the reference's Device::Render (stack-limit set-up, managed allocation, Kernel<<<>>>, synchronize) and returns its
 // wall-clock seconds in *seconds; film: width * height * 3 doubles, rows bottom-up.  The Device object is leaked on purpose:
 // its destructor frees an uninitialised member (Render's local `film` shadows it) and exits the process.
-int smallpt_ref_cuda_render(int width, int height, int samples_per_pixel, double* film_rgb, double* seconds)
+// base_stack_bytes > 0: the per-thread stack limit is set to this value BEFORE the reference's Render reads it and triples
+// it (smallpt_kernel.cpp:352-355).  As written -- the default 1024 bytes tripled -- the recursive FP64 Radiance overflows its
+// stack on sm_100a and the kernel faults ("an illegal memory access was encountered", observed on B200).
+int smallpt_ref_cuda_render(int width, int height, int samples_per_pixel, double* film_rgb, double* seconds, int base_stack_bytes)
 {
+    if (base_stack_bytes > 0)
+        cudaDeviceSetLimit(cudaLimitStackSize, (size_t)base_stack_bytes);
     Device* device = new Device;
     const auto t0 = std::chrono::steady_clock::now();
     Color* film = device->Render(width, height, samples_per_pixel);

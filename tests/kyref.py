@@ -183,14 +183,17 @@ def smallpt_cuda_available():
     return os.path.exists(os.path.join(REF_DIR, "libsmallpt_kernel_cuda_ref.so"))
 
 
-def smallpt_cuda(width, height, samples_per_pixel):
+def smallpt_cuda(width, height, samples_per_pixel, base_stack_bytes=0):
     """The reference's own CUDA kernel (smallpt_kernel.cu, built for sm_100a by oracle/ref/build_ref.sh): returns
-    (film[h, w, 3] float64 rows bottom-up, wall-clock seconds of its Device::Render).  Needs a GPU."""
+    (film[h, w, 3] float64 rows bottom-up, wall-clock seconds of its Device::Render).  Needs a GPU.  The reference's error
+    check exits the PROCESS on a CUDA error (and as written the kernel overflows its stack on B200): call it from a child
+    process (scripts/ref_cuda_smallpt.py)."""
     global _smallpt_cuda
     if _smallpt_cuda is None:
         _smallpt_cuda = C.CDLL(os.path.join(REF_DIR, "libsmallpt_kernel_cuda_ref.so"))
     out = np.zeros((height, width, 3), np.float64)
     sec = C.c_double(0)
-    rc = _smallpt_cuda.smallpt_ref_cuda_render(C.c_int(width), C.c_int(height), C.c_int(samples_per_pixel), out.ctypes.data_as(C.c_void_p), C.byref(sec))
+    rc = _smallpt_cuda.smallpt_ref_cuda_render(C.c_int(width), C.c_int(height), C.c_int(samples_per_pixel), out.ctypes.data_as(C.c_void_p), C.byref(sec),
+                                               C.c_int(base_stack_bytes))
     assert rc == 0
     return out, sec.value
