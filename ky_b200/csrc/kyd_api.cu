@@ -365,7 +365,7 @@ size_t wave_bytes_per_path(const WavefrontPlan& plan, int n_lights)
     if (plan.nee && !plan.pair_kernel) b += (size_t)n_lights * (128 + 2 * 4);   // light-sampling lines + pair queues
     if (plan.pair_kernel) b += (size_t)n_lights * 16;          // k_nee results
     if (plan.split || plan.pair_kernel) b += 96;               // vertex records
-    return b;
+    return b;   // (+ 32 bytes per level for the recursive integrators, added by the caller)
 }
 
 int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cudaStream_t stream, bool timed)
@@ -377,8 +377,10 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
     rp.lighting = d->lighting; rp.sampler = d->sampler; rp.seed = d->seed; rp.flags = d->flags;
     rp.weight = (float)(1. / d->spp);
 
+    const bool recursion = d->integrator == KYD_INT_SIMPLE_PT_RECURSION || d->integrator == KYD_INT_PT_RECURSION || d->integrator == KYD_INT_PT_RECURSION_DEFERED;
+    // (the recursive integrators' wavefront form needs constant-memory scenes: large scenes keep the per-pixel kernel)
     const bool wavefront = !(d->flags & KYD_FLAG_FUSED) &&
-        (d->integrator == KYD_INT_PT_ITERATION || d->integrator == KYD_INT_DIRECT_LIGHTING);
+        (d->integrator == KYD_INT_PT_ITERATION || d->integrator == KYD_INT_DIRECT_LIGHTING || (recursion && !ctx->scene.bvh_nodes));
     int64_t capacity = 0;
     if (wavefront)
     {
@@ -398,7 +400,14 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         // still fails is retried with half the wave down to 64 Ki paths.
         const int nee_units = plan.pair_kernel ? 1 : 8;
         const bool vertex = plan.split || plan.pair_kernel;
-        if (ctx->wave.capacity < capacity || ctx->wave.max_lights < nee_lights || (nee_lights > 0 && ctx->wave.nee_units < nee_units) ||
+        const int levels = plan.recursion ? d->max_depth + 1 : 0;
+        if (levels > 0)
+        {
+            // level records: 32 bytes per level and path; keep them below ~6 GB by shrinking the wave
+            const int64_t fit = (int64_t)6 << 30 >> 5;
+            if (capacity > fit / levels) capacity = fit / levels < 65536 ? 65536 : fit / levels;
+        }
+        if (ctx->wave.max_levels < levels || ctx->wave.capacity < capacity || ctx->wave.max_lights < nee_lights || (nee_lights > 0 && ctx->wave.nee_units < nee_units) ||
             (vertex && !ctx->wave.has_vertex))
         {
             size_t free_b = 0, total_b = 0;
@@ -410,7 +419,7 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
             }
             for (;;)
             {
-                const cudaError_t e = (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, nee_lights, nee_units, vertex);
+                const cudaError_t e = (cudaError_t)ensure_wave_buffers(ctx->wave, capacity, nee_lights, nee_units, vertex, levels);
                 if (e == cudaSuccess) break;
                 cudaGetLastError();   // clear the sticky-free allocation error
                 if (e != cudaErrorMemoryAllocation || capacity <= 65536)

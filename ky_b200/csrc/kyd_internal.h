@@ -32,6 +32,8 @@ struct WaveBuffers
     float4* path = nullptr;       // one 64-byte record (4 float4) per path slot
     float4* vertex = nullptr;     // 6 float4 per path slot: vertex record of the split light-sample stage
     float4* nee = nullptr;        // one 128-byte line per (light, path slot): the two NEE queries, vertex beta, result
+    float4* levels = nullptr;     // recursive integrators: 2 float4 per (level, path slot), level-major: {Lo.rgb, |cos|}, {f.rgb, pdf}
+    int max_levels = 0;           // levels that buffer was sized for (0: not allocated)
     // queues of path slots
     int* queue_a = nullptr;        // ray queues (ping-pong by bounce parity)
     int* queue_b = nullptr;
@@ -87,6 +89,7 @@ struct WavefrontPlan
     bool nee;             // the shadow stage runs (light-sampling lines are written)
     bool split;           // KYD_FLAG_SPLIT_LIGHT_SAMPLE: vertex records for the stand-alone light-sample kernel
     bool pair_kernel;     // hot with several lights: the light loop runs in k_nee over (vertex, light) pairs (vertex records + 16-byte results)
+    bool recursion;       // one of the three recursive integrators: forward pass with a per-level record, then k_unwind
     bool fused;           // inline_queries and not KYD_FUSE_INTERSECT=0: shade also traces the path's next ray (closest hit, lobe
                           // classification), so only the camera rays go through the intersect kernel
 };
@@ -96,9 +99,10 @@ inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scen
     const bool direct_only = rp.integrator == KYD_INT_DIRECT_LIGHTING;
     p.split = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) != 0;
     // (large scenes run the general kernels only: the specialised ones are not built for them)
-    p.hot = !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG && !p.split && scene.bvh_nodes == nullptr;
+    p.recursion = rp.integrator == KYD_INT_SIMPLE_PT_RECURSION || rp.integrator == KYD_INT_PT_RECURSION || rp.integrator == KYD_INT_PT_RECURSION_DEFERED;
+    p.hot = !p.recursion && !direct_only && rp.direct_sample == KYD_DS_BOTH_MIS && rp.sampler != KYD_SAMPLER_DEBUG && !p.split && scene.bvh_nodes == nullptr;
     p.inline_queries = p.hot && scene.n_lights == 1;
-    p.nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0 && !p.inline_queries;
+    p.nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0 && !p.inline_queries && !p.recursion;   // (recursion: light queries inside shade)
     p.pair_kernel = p.hot && p.nee;
     static const bool fuse_enabled = !(getenv("KYD_FUSE_INTERSECT") && getenv("KYD_FUSE_INTERSECT")[0] == '0');
     p.fused = p.inline_queries && fuse_enabled;
@@ -108,7 +112,7 @@ inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scen
 void free_wave_buffers(WaveBuffers& w);
 // (re)allocates the wavefront buffers for `capacity` path slots; light-sampling lines for `nee_lights` lights (0: none
 // needed) and vertex records only if `vertex`; returns a cudaError_t
-int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int nee_units, bool vertex);
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int nee_units, bool vertex, int levels = 0);
 
 // wavefront path: path_tracing_iteration_t and direct_lighting_t.  Adds to `launches` the kernels it launched.
 void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, WaveBuffers& w, int64_t wave_paths, float* film_dev, DevCounters* counters,

@@ -772,7 +772,7 @@ static cudaError_t alloc_array(T** p, size_t count)
 
 void free_wave_buffers(WaveBuffers& w)
 {
-    void* ptrs[] = { w.path, w.vertex, w.nee, w.queue_a, w.queue_b, w.queue_lobe[0][0], w.queue_lobe[0][1], w.queue_lobe[0][2], w.queue_lobe[0][3],
+    void* ptrs[] = { w.path, w.vertex, w.nee, w.levels, w.queue_a, w.queue_b, w.queue_lobe[0][0], w.queue_lobe[0][1], w.queue_lobe[0][2], w.queue_lobe[0][3],
                      w.queue_lobe[1][0], w.queue_lobe[1][1], w.queue_lobe[1][2], w.queue_lobe[1][3],
                      w.queue_nee[0], w.queue_nee[1], w.queue_pair[0], w.queue_pair[1] };
     for (void* p : ptrs)
@@ -780,11 +780,13 @@ void free_wave_buffers(WaveBuffers& w)
     w = WaveBuffers{};
 }
 
-int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int nee_units, bool vertex)
+int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int nee_units, bool vertex, int levels)
 {
-    if (w.capacity >= capacity && w.max_lights >= nee_lights && (nee_lights == 0 || w.nee_units >= nee_units) && (w.has_vertex || !vertex))
+    if (w.capacity >= capacity && w.max_lights >= nee_lights && (nee_lights == 0 || w.nee_units >= nee_units) && (w.has_vertex || !vertex) &&
+        w.max_levels >= levels)
         return cudaSuccess;
     if (capacity < w.capacity) capacity = w.capacity;
+    if (levels < w.max_levels) levels = w.max_levels;
     if (nee_lights < w.max_lights) nee_lights = w.max_lights;
     if (nee_units < w.nee_units) nee_units = w.nee_units;
     vertex = vertex || w.has_vertex;
@@ -795,6 +797,7 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int ne
     ok(alloc_array(&w.path, 4 * P));
     if (vertex) ok(alloc_array(&w.vertex, 6 * P));
     if (L > 0) ok(alloc_array(&w.nee, (size_t)nee_units * L * P));
+    if (levels > 0) ok(alloc_array(&w.levels, 2 * (size_t)levels * P));
     ok(alloc_array(&w.queue_a, P)); ok(alloc_array(&w.queue_b, P));
     for (int c = 0; c < 8; ++c) ok(alloc_array(&w.queue_lobe[c >> 2][c & 3], P));
     for (int c = 0; c < 2; ++c) ok(alloc_array(&w.queue_nee[c], P));
@@ -809,6 +812,7 @@ int ensure_wave_buffers(WaveBuffers& w, int64_t capacity, int nee_lights, int ne
     w.max_lights = nee_lights;
     w.nee_units = L > 0 ? nee_units : 0;
     w.has_vertex = vertex;
+    w.max_levels = levels;
     return cudaSuccess;
 }
 
@@ -830,6 +834,15 @@ static void launch_shade_one_light(bool fused, int grid, cudaStream_t stream, co
 {
     if (fused) launch_shade_lobes<TRAITS, true, NL_ONE, true>(grid, stream, wp, w, counters, bounce);
     else launch_shade_lobes<TRAITS, true, NL_ONE, false>(grid, stream, wp, w, counters, bounce);
+}
+
+template <int INTEGRATOR>
+static void launch_shade_rec(int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w, DevCounters* counters, int bounce)
+{
+    k_shade_rec<LOBE_LAMBERT, INTEGRATOR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade_rec<LOBE_PHONG, INTEGRATOR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade_rec<LOBE_MIRROR, INTEGRATOR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
+    k_shade_rec<LOBE_FRESNEL, INTEGRATOR><<<grid, SHADE_THREADS, 0, stream>>>(wp, w, counters, bounce);
 }
 
 static void launch_shade(int traits, bool hot, bool one_light, bool fused, int grid, cudaStream_t stream, const WaveParams& wp, const WaveBuffers& w,
@@ -924,6 +937,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
             wp.no_pending = nee ? 0 : 1;
             wp.pair_kernel = plan.pair_kernel ? 1 : 0;
+            wp.recursion = plan.recursion ? rp.integrator : 0;
 
             // queue tails start at zero; the camera rays are generated inside the first intersect launch
             cudaMemsetAsync(counters->queue, 0, sizeof(counters->queue), stream);
@@ -942,7 +956,16 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                 if (plan.fused)   // the lobe queues the shade kernels of this bounce fill were consumed one bounce ago
                     cudaMemsetAsync(&counters->queue[Q_LOBE0 + 4 * ((bounce & 1) ^ 1)], 0, 4 * sizeof(unsigned long long), stream);
                 T(StageTimer::SHADE);
-                launch_shade(traits, hot, plan.inline_queries, plan.fused, grid128, stream, wp, w, counters, bounce);
+#if !KYD_BIG_SCENE
+                if (plan.recursion)
+                {
+                    if (rp.integrator == KYD_INT_SIMPLE_PT_RECURSION) launch_shade_rec<KYD_INT_SIMPLE_PT_RECURSION>(grid128, stream, wp, w, counters, bounce);
+                    else if (rp.integrator == KYD_INT_PT_RECURSION) launch_shade_rec<KYD_INT_PT_RECURSION>(grid128, stream, wp, w, counters, bounce);
+                    else launch_shade_rec<KYD_INT_PT_RECURSION_DEFERED>(grid128, stream, wp, w, counters, bounce);
+                }
+                else
+#endif
+                    launch_shade(traits, hot, plan.inline_queries, plan.fused, grid128, stream, wp, w, counters, bounce);
                 T(-1);
                 *launches += 4;
                 if (plan.pair_kernel)
@@ -983,6 +1006,11 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                 }
             }
             T(StageTimer::ACCUMULATE);
+            if (plan.recursion)
+            {
+                k_unwind<<<grid256, 256, 0, stream>>>(wp, w);   // the recursion's return path, into the slot k_accumulate reads
+                ++*launches;
+            }
             k_accumulate<<<grid256, 256, 0, stream>>>(wp, w, film_dev);
             T(-1);
             ++*launches;

@@ -69,6 +69,10 @@ enum { V_POSITION = 0, V_NORMAL = 1, V_WO = 2, V_COLOR = 3, V_RNG = 4, V_BETA = 
 enum { FLAG_PREV_SPECULAR = 1, FLAG_SURFACE_SHIFT = 4, FLAG_SURFACE_MASK = 0xfff << 4, FLAG_PENDING_SHIFT = 16, FLAG_PENDING_MASK = (int)0xffff0000u };
 // entry of the pair queues: path slot | light << 24 (a wave holds at most 2^24 paths, a scene at most 16 lights)
 enum { PAIR_LIGHT_SHIFT = 24, PAIR_SLOT_MASK = (1 << 24) - 1 };
+// The recursive integrators (wp.recursion) trace their light queries inside shade, so no light is ever pending: the 16 bits
+// hold the recursion depth of the vertex (bits 16-23) and, once the path has ended, its number of levels (bits 24-31).
+enum { FLAG_DEPTH_SHIFT = 16, FLAG_DEPTH_MASK = 0xff << 16, FLAG_LEVELS_SHIFT = 24 };
+
 // flags word of a light-sampling line (w of the light query's direction unit)
 // (bits 8..: 1 + the light's surface when the BSDF-sampled query is in its occlusion form, NeeRay::light_surface)
 // (NEE_LIGHT_LIVE: the light-sampled query has to be traced.  Its tmax cannot say so: a light point closer than 2e-3 -- a
@@ -86,6 +90,7 @@ struct WaveParams
     int direct_only;          // direct_lighting_t: stop after the first vertex' light loop
     int split_light_sample;   // light-sample as its own kernel (KYD_FLAG_SPLIT_LIGHT_SAMPLE) instead of inside shade
     int no_pending;           // light queries are traced inside shade (one light, headline kernels): no path ever carries pending Ld
+    int recursion;            // 0, or the recursive integrator being rendered (KYD_INT_*_RECURSION*): per-level records + k_unwind
     int pair_kernel;          // headline configuration with several lights: the light loop runs in k_nee, one thread per (vertex, light);
                               // results are 16 bytes per pair at [slot * n_lights + light] of the light-sampling buffer, every light of
                               // a vertex has one, and the vertex' beta is read from its vertex record
@@ -94,6 +99,8 @@ struct WaveParams
 KYD_DEV float4* path_line(const WaveBuffers& w, int slot) { return w.path + (size_t)slot * PATH_UNITS; }
 KYD_DEV float4* nee_line(const WaveBuffers& w, long long plane, int light, int slot) { return w.nee + ((size_t)light * plane + slot) * NEE_UNITS; }
 KYD_DEV float4* vertex_line(const WaveBuffers& w, int slot) { return w.vertex + (size_t)slot * VERTEX_UNITS; }
+// record of one recursion level of a path (recursive integrators): {Lo.rgb, |cos|}, {f.rgb, pdf}; level-major planes
+KYD_DEV float4* level_line(const WaveBuffers& w, long long plane, int level, int slot) { return w.levels + ((size_t)level * plane + slot) * 2; }
 
 KYD_DEV void flush_counters(unsigned rays, unsigned traced, DevCounters* counters)
 {
@@ -381,6 +388,25 @@ __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(Wav
                 // sector 0 goes back whole, now carrying the hit
                 store_path_ray(p, r.o, t, r.d, (flags & (FLAG_PREV_SPECULAR | FLAG_PENDING_MASK)) | ((s + 1) << FLAG_SURFACE_SHIFT));
                 lobe = classify_lobe(s, r, t);
+            }
+            else if (wp.recursion)
+            {
+                // a ray of a recursive integrator that leaves the scene ends the recursion: this level returns the environment's
+                // radiance -- always (simple_path_tracing_recursion_t, ky.cpp:4207-4208), or where the level adds emitted
+                // light at all (depth 0, or after a specular bounce in the deferred form; ky.cpp:4326-4336, 4445-4455)
+                const int depth = CAMERA ? 0 : (flags & FLAG_DEPTH_MASK) >> FLAG_DEPTH_SHIFT;
+                float3 Lo_level = environment_lighting();
+                if (wp.recursion != KYD_INT_SIMPLE_PT_RECURSION)
+                {
+                    const bool deferred = wp.recursion == KYD_INT_PT_RECURSION_DEFERED;
+                    const bool adds = depth == 0 || (deferred && (flags & FLAG_PREV_SPECULAR));
+                    const bool keep = !deferred || (depth == 0 ? (wp.rp.lighting & KYD_LIGHTING_EMIT) : (wp.rp.lighting & KYD_LIGHTING_INDIRECT)) != 0;
+                    Lo_level = adds ? add(KYD_BLACK, keep ? Lo_level : KYD_BLACK) : KYD_BLACK;
+                }
+                float4* lv = level_line(w, wp.plane, depth, slot);
+                lv[0] = make_float4(Lo_level.x, Lo_level.y, Lo_level.z, 0.f);
+                lv[1] = make_float4(0.f, 0.f, 0.f, 1.f);
+                store_path_ray(p, r.o, o.w, r.d, (depth + 1) << FLAG_LEVELS_SHIFT);
             }
             else if (CAMERA)
             {
@@ -1268,6 +1294,180 @@ __global__ void __launch_bounds__(256) k_shadow(WaveParams wp, WaveBuffers w, De
         }
     }
     flush_counters(rays, traced, counters);
+}
+
+// ---- the three recursive integrators in wavefront form (ky.cpp:4191-4238, 4305-4402, 4409-4514) ---------------------------
+// A recursion level returns  Lo_level + ((f * Li_deeper) * |cos|) / pdf  (ky.cpp:4233, 4400, 4512).  The forward pass is the
+// iterative loop -- intersect, shade per lobe -- with the level's (Lo_level, f, |cos|, pdf) written to a record instead of a
+// running throughput; k_unwind then applies the expression from the deepest level outwards, which is the recursion's FP32
+// evaluation order.  Light queries are traced inside shade (no lines, no pending state); what differs between the three is
+// spelled out at the reference lines cited below.
+KYD_DEV float3 sample_all_light_inline(const HitGeom& g, const Bsdf& b, Sampler& smp, int ds, ShadeCounts* counts) // ky.cpp:3834-3872
+{
+    float3 Ld = KYD_BLACK;
+    const int n = c_scene.n_lights;
+    for (int l = 0; l < n; ++l)
+    {
+        NeeRay qb, ql;
+        light_sample_pair<TRAITS_ANY>(ds, g, b, l, smp, &qb, &ql);
+        counts->ref_rays += (qb.ref_query ? 1u : 0u) + (ql.ref_query ? 1u : 0u);
+        Ld = add(Ld, nee_resolve_pair(ds, qb, ql, counts));
+        smp.skip(4 + ((ds == KYD_DS_BSDF && !light_is_delta(c_scene.lights[l].kind)) ? 2 : 0));
+    }
+    return Ld;
+}
+
+// russian roulette shared by the three (ky.cpp:4219-4226, 4389-4397, 4501-4509)
+KYD_DEV bool recursion_roulette_wf(Sampler& smp, int* depth, BsdfSample* bs)
+{
+    if (++*depth > 3)
+    {
+        const float m = max_component(bs->f);
+        if (smp.get_float() < m)
+            bs->f = mul(bs->f, 1 / m);
+        else
+            return false;
+    }
+    return true;
+}
+
+template <int LOBE, int INTEGRATOR>
+__global__ void __launch_bounds__(SHADE_THREADS, 3) k_shade_rec(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
+{
+    constexpr bool SIMPLE = INTEGRATOR == KYD_INT_SIMPLE_PT_RECURSION, DEFERRED = INTEGRATOR == KYD_INT_PT_RECURSION_DEFERED;
+    stage_rects();
+    const int parity = bounce & 1;
+    const int n = (int)counters->queue[Q_LOBE0 + 4 * parity + LOBE];
+    const int* __restrict__ queue = w.queue_lobe[parity][LOBE];
+    int* __restrict__ next_queue = parity ? w.queue_a : w.queue_b;
+    unsigned long long* const tails[1] = { &counters->queue[Q_RAY0 + (parity ^ 1)] };
+    int* const out_queues[1] = { next_queue };
+    const int stride = gridDim.x * blockDim.x;
+    const int ds = wp.rp.direct_sample, lighting = wp.rp.lighting, max_depth = wp.rp.max_depth;
+    WarpPush<1> push;
+    push.init();
+    ShadeCounts counts = { 0u, 0u };
+    long long ia = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride, ia += stride) // block-uniform trip count
+    {
+        bool alive = false;
+        int slot = 0;
+        if (ia < n)
+        {
+            slot = queue[ia];
+            float4* p = path_line(w, slot);
+            PathState st;
+            unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
+            Ray r;
+            r.o = st.o; r.d = st.d; r.tmax = KYD_INF;
+            const int surface = st.surface();
+            const int depth = (st.flags & FLAG_DEPTH_MASK) >> FLAG_DEPTH_SHIFT;
+            const bool prev_specular = (st.flags & FLAG_PREV_SPECULAR) != 0;
+            const HitGeom g = shape_hit_geom(surface_shape(surface), r, st.t);
+            const float3 emission = surface_emission(surface, g);
+            Bsdf b;
+            material_scattering(c_scene.materials[surface_material(surface)], g, &b);   // (the lobe is LOBE: classify_lobe made the same choice)
+            Sampler smp;
+            smp.debug = wp.rp.sampler == KYD_SAMPLER_DEBUG;
+            smp.state = st.rng;
+
+            float3 Lo = KYD_BLACK, f = KYD_BLACK;
+            float a = 0.f, pdf = 1.f;
+            Ray next = r;
+            int next_depth = depth;
+            bool next_specular = false;
+            if (SIMPLE)
+            {
+                // ky.cpp:4201-4237: emission at every level; no light sampling; the next ray starts ON the surface (ky.cpp:4232)
+                Lo = emission;
+                if (depth < max_depth)
+                {
+                    BsdfSample bs = bsdf_sample(b, g.wo, smp.get_float2());
+                    if (!(is_black(bs.f) || bs.pdf == 0.f) && recursion_roulette_wf(smp, &next_depth, &bs))
+                    {
+                        f = bs.f; a = abs_dot(bs.wi, g.normal); pdf = bs.pdf;
+                        next.o = g.position; next.d = bs.wi;
+                        alive = true;
+                    }
+                }
+            }
+            else
+            {
+                // ky.cpp:4321-4401 (path_tracing_recursion_t) and 4440-4513 (deferred form, with render_lighting_enum's filter)
+                if (depth == 0 || (DEFERRED && prev_specular))
+                {
+                    const bool keep = !DEFERRED || (depth == 0 ? (lighting & KYD_LIGHTING_EMIT) : (lighting & KYD_LIGHTING_INDIRECT)) != 0;
+                    Lo = add(Lo, keep ? emission : KYD_BLACK);
+                }
+                if (depth < max_depth)
+                {
+                    const bool delta = bsdf_is_delta(b.lobe);
+                    if (!delta)
+                    {
+                        const float3 Ld = sample_all_light_inline(g, b, smp, ds, &counts);
+                        const bool keep = !DEFERRED || (depth == 0 ? (lighting & KYD_LIGHTING_DIRECT) : (lighting & KYD_LIGHTING_INDIRECT)) != 0;
+                        Lo = add(Lo, keep ? Ld : KYD_BLACK);
+                    }
+                    else if (!DEFERRED)
+                    {
+                        // a specular vertex looks for emitted light along its own sample, from ON the surface (ky.cpp:4340-4350)
+                        const BsdfSample bs = bsdf_sample(b, g.wo, smp.get_float2());
+                        Ray wi_ray;
+                        wi_ray.o = g.position; wi_ray.d = bs.wi; wi_ray.tmax = KYD_INF;
+                        float t;
+                        const int s = wf_closest(wi_ray, &t);
+                        counts.ref_rays++;
+                        counts.traced++;
+                        const float3 Le = s < 0 ? environment_lighting() : surface_emission(s, shape_hit_geom(surface_shape(s), wi_ray, t));
+                        Lo = add(Lo, cdiv(mul(cmulc(bs.f, Le), abs_dot(bs.wi, g.normal)), bs.pdf));
+                    }
+                    BsdfSample bs = bsdf_sample(b, g.wo, smp.get_float2());
+                    if (!(is_black(bs.f) || bs.pdf == 0.f) && recursion_roulette_wf(smp, &next_depth, &bs))
+                    {
+                        f = bs.f; a = abs_dot(bs.wi, g.normal); pdf = bs.pdf;
+                        if (DEFERRED) { next.o = g.position; next.d = bs.wi; }   // no origin offset, ky.cpp:4511
+                        else next = spawn_ray(g, bs.wi);                          // ky.cpp:4399
+                        next_specular = delta;
+                        alive = true;
+                    }
+                }
+            }
+            float4* lv = level_line(w, wp.plane, depth, slot);
+            lv[0] = make_float4(Lo.x, Lo.y, Lo.z, a);
+            lv[1] = make_float4(f.x, f.y, f.z, pdf);
+            if (alive)
+                store_path_ray(p, next.o, KYD_INF, next.d, (next_specular ? FLAG_PREV_SPECULAR : 0) | (next_depth << FLAG_DEPTH_SHIFT));
+            else
+                store_path_ray(p, r.o, KYD_INF, r.d, (depth + 1) << FLAG_LEVELS_SHIFT);
+            store_path_tail(p, st.beta, st.Lo, smp.state);
+        }
+        push.commit(out_queues);
+        push.reserve(alive ? 1u : 0u, slot, tails);
+    }
+    push.commit(out_queues);
+    flush_counters(counts.ref_rays, counts.traced, counters);
+}
+
+// the recursion's return path: result = Lo_n + ((f_n * result) * |cos|_n) / pdf_n from the deepest level outwards; the value
+// lands where k_accumulate expects a path's radiance
+__global__ void __launch_bounds__(256) k_unwind(WaveParams wp, WaveBuffers w)
+{
+    const int stride = gridDim.x * blockDim.x;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < wp.nslots; slot += stride)
+    {
+        float4* p = path_line(w, slot);
+        const int levels = (int)((unsigned)__float_as_int(p[P_DIRECTION].w) >> FLAG_LEVELS_SHIFT);
+        float3 result = KYD_BLACK;
+        for (int n = levels - 1; n >= 0; --n)
+        {
+            const float4* lv = level_line(w, wp.plane, n, slot);
+            const float4 l0 = lv[0], l1 = lv[1];
+            const float3 Lo = V3(l0.x, l0.y, l0.z);
+            result = n == levels - 1 ? Lo : add(Lo, cdiv(mul(cmulc(V3(l1.x, l1.y, l1.z), result), l0.w), l1.w));
+        }
+        const float4 tail = p[P_TAIL];
+        store_path_tail(p, V3(1.f, 1.f, 1.f), result, (unsigned long long)__float_as_uint(tail.z) | ((unsigned long long)__float_as_uint(tail.w) << 32));
+    }
 }
 
 // ---- accumulate: film_t::add_color order -- L = L + Li * (1/spp) sample after sample (ky.cpp:3717-3721) ------
