@@ -555,6 +555,7 @@ def main():
         if dom == 2 and job.shade[0] > 0:
             # shade: gathers a 64-byte path record per vertex and rewrites it (+4 B queue entry in, +4..8 B out); multi-light
             # scenes also write 64-byte light-sampling lines
+            # (shade[1]: light-sampling lines written for the shadow stage, 64 B each; with k_nee the counter holds (vertex, light) pairs)
             alg_bytes = 136 * job.shade[0] + 64 * job.shade[1]
             kshade = (ncu or {}).get("kernels", {}).get("k_shade<lambert>", {})
             roofline = {"bound": "hbm", "kernel": "k_shade<lobe> (4 launches per bounce)", "achieved": alg_bytes / (stage_ms[2] * 1e-3) / 1e9,
@@ -562,9 +563,10 @@ def main():
                         "traffic": kshade.get("dram_bytes"),
                         "algorithmic_bytes_per_step": alg_bytes / args.steps, "ms_per_step": stage_ms[2] / args.steps,
                         "note": f"peak = {peaks['source']} copy bandwidth; gather/scatter of 64-byte records through lobe-sorted queues "
-                                "(tools/membench.cu: 3.7-3.9 TB/s for that pattern); the kernel also traces the vertex' light queries and is "
-                                "issue-bound, not HBM-bound: see roofline_fp32_issue and ncu.kernels; traffic = dram bytes of ONE k_shade<lambert> "
-                                "launch of the committed capture (ncu.file), not of a whole step"}
+                                "(tools/membench.cu: 3.7-3.9 TB/s for that pattern); the kernel also traces the vertex' light queries and -- fused "
+                                "configuration -- the path's next ray, which adds instructions but no bytes, so it is issue-bound, not HBM-bound: "
+                                "see roofline_fp32_issue and ncu.kernels; traffic = dram bytes of ONE k_shade<lambert> launch of the committed "
+                                "capture (ncu.file), not of a whole step"}
         else:
             roofline = {"bound": "fp32_issue", "kernel": STAGES[dom], "achieved": flops_traced_all / (kernels_ms * 1e-3) / world / 1e12,
                         "peak": peak_lane_ops / 1e12, "unit": "TFLOP/s (FP32 lane-ops/s, FMA off)", "frac": frac_traced, "traffic": None}

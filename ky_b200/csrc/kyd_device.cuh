@@ -172,7 +172,11 @@ KYD_DEV bool rsqrt_ky_accept(float s, float yh, float rho)
     return s > 0x1p-60f && s < 0x1p60f && rho < hi && rho > lo;
 }
 
+#if defined(KYD_RSQRT_NOINLINE) && KYD_RSQRT_NOINLINE
+__device__ __noinline__ float rsqrt_ky(float s)
+#else
 KYD_DEV float rsqrt_ky(float s)
+#endif
 {
 #if defined(KYD_FAST_RSQRT) && !KYD_FAST_RSQRT
     return __double2float_rn(__drcp_rn(__dsqrt_rn((double)s)));
