@@ -916,12 +916,18 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
 #ifndef KYD_SHADE_PREFETCH_MANY
 #define KYD_SHADE_PREFETCH_MANY 1
 #endif
+#ifndef KYD_SHADE_PREFETCH_SPECULAR
+#define KYD_SHADE_PREFETCH_SPECULAR 0   // (measured: 2543 vs 2544 Msamples/s on C5, no effect)
+#endif
 #ifndef KYD_SHADE_PREFETCH
 #define KYD_SHADE_PREFETCH 0   // (1: +16 registers for the next record, spills in the one-light kernels; A/B in profiles/r02_ab_variants.txt)
 #endif
     // (the multi-light headline kernels hand their light loop to k_nee: what is left is short and waits for its record --
     // long-scoreboard stalls 14 per issue in profiles/r02_c3_*; they have the registers to load the next one early)
-    constexpr bool PREFETCH = HOT && ((NL == NL_ONE && KYD_SHADE_PREFETCH != 0) || (NL == NL_MANY && KYD_SHADE_PREFETCH_MANY != 0));
+    // (and the mirror / glass kernels: short, 93-105 registers, long-scoreboard 2.7-5 stalls per issue without it)
+    constexpr bool SPECULAR_LOBE = LOBE == LOBE_MIRROR || LOBE == LOBE_FRESNEL;
+    constexpr bool PREFETCH = HOT && ((NL == NL_ONE && (KYD_SHADE_PREFETCH != 0 || (SPECULAR_LOBE && KYD_SHADE_PREFETCH_SPECULAR != 0))) ||
+                                      (NL == NL_MANY && KYD_SHADE_PREFETCH_MANY != 0));
     long long ia = i;
     int slot_cur = ia < n ? queue[ia] : -1;
     int slot_next = ia + stride < n ? queue[ia + stride] : -1;

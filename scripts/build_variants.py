@@ -12,6 +12,7 @@ variants = {
     "nocull": ["-DKYD_NEE_CULL=0"],
     "powinline": ["-DKYD_POW_INLINE=1"],
     "rsqrtcall": ["-DKYD_RSQRT_NOINLINE=1"],
+    "specnopf": ["-DKYD_SHADE_PREFETCH_SPECULAR=0"],
     "neenopf": ["-DKYD_NEE_PREFETCH=0"],
     "manynopf": ["-DKYD_SHADE_PREFETCH_MANY=0"],
     "nee5": ["-DKYD_NEE_MIN_BLOCKS=5"],
