@@ -287,6 +287,29 @@ KYD_DEV unsigned long long mix64(unsigned long long z)
 #define KYD_LCG_C 0xBull
 #define KYD_LCG_MASK 0xFFFFFFFFFFFFull
 
+// k LCG steps are one: X -> (A^k X + C (A^(k-1) + ... + 1)) mod 2^48.  Row l = the jump over the 4 l draws the light loop
+// spends on the lights before light l (ky.cpp:3866-3868); generated by scripts, checked against the
+// step-by-step loop by tests/test_gpu_kat.py through every film of a multi-light scene.
+__constant__ unsigned long long c_lcg_jump4[17][2] = {
+    { 0x000000000001ull, 0x000000000000ull },
+    { 0x32EB772C5F11ull, 0x2D3873C4CD04ull },
+    { 0x75489F259F21ull, 0x7CBA449AE648ull },
+    { 0x199C3838D031ull, 0xD4CF89E2CFCCull },
+    { 0x6DC260740241ull, 0x0D0352014D90ull },
+    { 0xB05B0EB64551ull, 0x4C56A6636394ull },
+    { 0x35692EBFA961ull, 0x83F34BC255D8ull },
+    { 0x230D6E413E71ull, 0x9213C2A7A85Cull },
+    { 0xFAC6CAED1481ull, 0x1E4C4C311F20ull },
+    { 0x8633F1863B91ull, 0x40D8F714BE24ull },
+    { 0x18F17DF0C3A1ull, 0xAE50F8E4C968ull },
+    { 0xDCE22C41BCB1ull, 0x205FD793C4ECull },
+    { 0x8BEF0ACF36C1ull, 0x7F29273874B0ull },
+    { 0x231EBD4041D1ull, 0x5E03E011DCB4ull },
+    { 0x5FC3E09CEDE1ull, 0x6D8690CB40F8ull },
+    { 0xE973A05E4AF1ull, 0xD4ADF100257Cull },
+    { 0xAB768C7E6901ull, 0xF77B98004E40ull },
+};
+
 struct Sampler
 {
     unsigned long long state;
@@ -315,6 +338,12 @@ struct Sampler
         if (debug) return;
         for (int i = 0; i < n; ++i)
             state = (state * KYD_LCG_A + KYD_LCG_C) & KYD_LCG_MASK;
+    }
+    // skip(4 * lights), lights <= 16, in one step
+    KYD_DEV void skip_lights(int lights)
+    {
+        if (debug) return;
+        state = (state * c_lcg_jump4[lights][0] + c_lcg_jump4[lights][1]) & KYD_LCG_MASK;
     }
     // get_camera_sample's offset inside the pixel (ky.cpp:966-974): two draws, or -- KYD_SAMPLER_TRAPEZOIDAL -- smallpt's
     // tent filter on a 2x2 sub-pixel grid (smallpt2pbrt/smallpt_rewrite.cpp:449-466 in float; sub-pixel = sample / (spp / 4))

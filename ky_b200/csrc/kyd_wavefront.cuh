@@ -677,7 +677,8 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
                     *out_pairs = new_pending;
             }
             // sample_all_light draws 4 floats per light, plus 2 per non-delta light in `bsdf` mode
-            smp.skip(4 * n_lights + (ds == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
+            if (HOT) smp.skip_lights(n_lights);   // (both_mis: 4 per light, in one step)
+            else smp.skip(4 * n_lights + (ds == KYD_DS_BSDF ? 2 * c_scene.n_nondelta_lights : 0));
         }
 
         if (!direct_only)
@@ -1144,7 +1145,7 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
         Sampler smp;
         smp.debug = false;
         smp.state = (unsigned long long)__float_as_uint(rng4.x) | ((unsigned long long)__float_as_uint(rng4.y) << 32);
-        smp.skip(4 * l);                                 // both_mis: four draws per light (ky.cpp:3866-3868)
+        smp.skip_lights(l);                              // both_mis: four draws per light before this one (ky.cpp:3866-3868)
         const float2 random_bsdf = smp.get_float2();
         const float2 random_light = smp.get_float2();
         float3 Lb = KYD_BLACK, Ll = KYD_BLACK;
