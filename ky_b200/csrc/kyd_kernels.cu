@@ -975,14 +975,19 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
 #if !KYD_BIG_SCENE
                     if (traits == TRAITS_AREA_SPHERE)
                     {
+#if KYD_NEE_DEFER
                         k_nee<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
                         k_nee<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+#else
+                        k_nee_serial<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+#endif
                     }
                     else
 #endif
                     {
-                        k_nee<LOBE_LAMBERT, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
-                        k_nee<LOBE_PHONG, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_LAMBERT, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_PHONG, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
                     }
                     T(-1);
                     *launches += 2;

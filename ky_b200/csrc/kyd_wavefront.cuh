@@ -970,7 +970,9 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
             if (FUSE && v.alive)
             {
                 // scene_t::intersect for the next loop iteration of path_tracing_iteration_t::Li (ky.cpp:4542)
-                if (!v.traced)
+                // (the one-light headline kernels trace every continuation themselves, in the third trip of their loop: without
+                // the constant, a second, never executed copy of the walk sits in the middle of an instruction-fetch bound kernel)
+                if (!HOT_ONE && !v.traced)
                 {
                     Ray nr;
                     nr.o = v.o; nr.d = v.d; nr.tmax = KYD_INF;
@@ -1100,10 +1102,171 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 #define KYD_NEE_PREFETCH 0   // (L2 prefetch of the next vertex record: 703 vs 747 Msamples/s on C3 -- the records are already L1/L2 hits, the extra requests only compete)
 #endif
 #ifndef KYD_NEE_MIN_BLOCKS
-#define KYD_NEE_MIN_BLOCKS 5   // 94 registers, 20 warps per SM (A/B in profiles/r02_ab_variants.txt: 4 -> 705, 5 -> 747, 6 -> 716, 8 -> 696 Msamples/s on C3)
+#define KYD_NEE_MIN_BLOCKS 6   // the deferred form fits 80 registers without spills: 24 warps per SM (5 -> 829.5, 6 -> 839.2 Msamples/s on C3)
 #endif
+#ifndef KYD_NEE_SERIAL_MIN_BLOCKS
+#define KYD_NEE_SERIAL_MIN_BLOCKS 5   // 94 registers, 20 warps per SM (A/B in profiles/r02_ab_variants.txt: 4 -> 705, 5 -> 747, 6 -> 716, 8 -> 696 Msamples/s on C3)
+#endif
+#ifndef KYD_NEE_DEFER
+#define KYD_NEE_DEFER 1
+#endif
+#ifndef KYD_NEE_LIGHT_MAJOR
+#define KYD_NEE_LIGHT_MAJOR 1
+#endif
+#if KYD_NEE_DEFER
+// Deferred BSDF-sampled queries.  bsdf_query_certainly_misses settles all but a few per cent of a sphere light's
+// BSDF-sampled queries, but a warp holds 32 pairs: with a survivor in most warps, nearly every warp walked the exact set-up
+// (double-precision sincos, IEEE divisions and square roots, the sphere test, pdf_Li) and the query's traversal with ~5 of
+// its 32 lanes busy -- a quarter of the kernel's issue slots.  Here a pair whose BSDF-sampled query survives the cull is
+// parked in a per-warp shared-memory list together with its finished light-sampled half, and the warp runs the exact path
+// on a FULL batch of 32 parked pairs whenever it has one (and once more for the rest when it runs out of new pairs).  Every
+// iteration of the loop is, for the whole warp, either "32 new pairs" or "32 parked pairs": they share the record load, the
+// frame set-up and -- through the NeeRay both produce -- one copy of the closest-hit walk.  The pair's value is the same
+// expression of the same operands, 0.5 Lb + 0.5 Ll (ky.cpp:4083), whichever iteration writes it.
 template <int LOBE, int TRAITS>
 __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
+{
+    stage_rects();
+    __shared__ float4 s_parked[4][64];                   // {Ll.rgb, pair index}: < 32 left over + up to 32 new per iteration
+    const int n = (int)counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)];
+    const int* __restrict__ queue = w.queue_nee[LOBE == LOBE_PHONG];
+    const int n_lights = c_scene.n_lights;
+    const int total = n * n_lights;                      // (<= 2^24 paths x 16 lights)
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    float4* parked = s_parked[threadIdx.x >> 5];
+    int n_parked = 0;                                    // warp-uniform
+    // A warp's new pairs are 32 VERTICES x ONE light, the vertex group's lights in consecutive iterations: the light's data
+    // (constant memory, indexed by l) is then one address per warp instead of five -- a constant load with several
+    // addresses in a warp is replayed once per address -- and the group's records are L1 hits after the first light.
+    // (KYD_NEE_LIGHT_MAJOR=0: the lights of a vertex in adjacent lanes, one broadcast load of the record)
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const int n_groups = KYD_NEE_LIGHT_MAJOR ? (n + 31) >> 5 : (total + 31) >> 5;
+    int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int l_fresh = 0;
+    unsigned rays = 0, traced = 0;
+    for (;;)
+    {
+        const bool fresh = n_parked < 32 && group < n_groups; // warp-uniform: new pairs while there are any and no full batch waits
+        if (!fresh && n_parked == 0)
+            break;
+        int pair = -1;                                   // vertex | light << 24
+        float3 Ll = KYD_BLACK;
+        if (fresh)
+        {
+            if (KYD_NEE_LIGHT_MAJOR)
+            {
+                const int vertex = group * 32 + lane;
+                if (vertex < n)
+                    pair = vertex | (l_fresh << PAIR_LIGHT_SHIFT);
+                if (++l_fresh == n_lights)
+                {
+                    l_fresh = 0;
+                    group += warps_total;
+                }
+            }
+            else
+            {
+                const int idx = group * 32 + lane;
+                if (idx < total)
+                    pair = (idx / n_lights) | ((idx % n_lights) << PAIR_LIGHT_SHIFT);
+                group += warps_total;
+            }
+        }
+        else
+        {
+            const int first = n_parked >= 32 ? n_parked - 32 : 0;
+            if (first + lane < n_parked)
+            {
+                const float4 e = parked[first + lane];
+                pair = __float_as_int(e.w);
+                Ll = V3(e.x, e.y, e.z);
+            }
+            n_parked = first;
+        }
+        __syncwarp();
+        bool park = false;
+        if (pair >= 0)
+        {
+            const int vertex = pair & PAIR_SLOT_MASK;
+            const int l = pair >> PAIR_LIGHT_SHIFT;
+            const int slot = queue[vertex];
+            const float4* v = vertex_line(w, slot);
+            const float4 p4 = v[V_POSITION], n4 = v[V_NORMAL], wo4 = v[V_WO], c4 = v[V_COLOR], rng4 = v[V_RNG], vb = v[V_BETA];
+            HitGeom g;
+            g.position = V3(p4.x, p4.y, p4.z);
+            g.normal = V3(n4.x, n4.y, n4.z);
+            g.wo = V3(wo4.x, wo4.y, wo4.z);
+            Bsdf b;
+            b.f.s = V3(p4.w, wo4.w, c4.w);
+            b.f.t = V3(rng4.z, rng4.w, vb.w);
+            b.f.n = normalize(g.normal);                 // frame_t's z axis (ky.cpp:537-541)
+            b.a = V3(c4.x, c4.y, c4.z);
+            b.t = KYD_BLACK;
+            b.eta_t = 1.f;
+            b.exponent = n4.w;
+            b.lobe = LOBE;
+
+            Sampler smp;
+            smp.debug = false;
+            smp.state = (unsigned long long)__float_as_uint(rng4.x) | ((unsigned long long)__float_as_uint(rng4.y) << 32);
+            smp.skip_lights(l);                          // both_mis: four draws per light before this one (ky.cpp:3866-3868)
+            const float2 random_bsdf = smp.get_float2();
+            NeeRay q;
+            if (fresh)
+            {
+                // the BSDF-sampled half is settled here only if it certainly misses (the reference still traces that ray)
+                park = !(KYD_NEE_CULL && bsdf_query_certainly_misses<TRAITS>(g, b, l, random_bsdf));
+                rays += park ? 0u : 1u;
+                const float2 random_light = smp.get_float2();
+                q = nee_light_setup<TRAITS, KYD_NEE_CULL != 0>(g, b, l, random_light, true);              // ky.cpp:4035-4074
+            }
+            else
+                q = nee_bsdf_setup<TRAITS, false>(g, b, l, random_bsdf, true);                            // ky.cpp:3968-4033
+            rays += q.ref_query ? 1u : 0u;
+            float3 value = KYD_BLACK;
+            if (q.active)
+            {
+                traced++;
+                float t;
+                if (!fresh && q.light_surface < 0)
+                {
+                    // closest-hit form (a light carried by several surfaces, or the environment light)
+                    const int s = wf_closest(q.ray, &t);
+                    value = nee_bsdf_resolve(q, s, t);
+                }
+                else
+                {
+                    const int s = wf_closest_from(q.ray, q.light_surface, &t);
+                    value = (fresh ? s < 0 : s == q.light_surface) ? q.value : KYD_BLACK;
+                }
+            }
+            const float3 Lb = fresh ? KYD_BLACK : value;
+            if (fresh)
+                Ll = value;
+            if (!park)
+            {
+                const float3 e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
+                w.nee[(size_t)slot * n_lights + l] = make_float4(e.x, e.y, e.z, 0.f);
+            }
+        }
+        if (fresh)
+        {
+            const unsigned m = __ballot_sync(0xffffffffu, park);
+            if (park)
+                parked[n_parked + __popc(m & lt)] = make_float4(Ll.x, Ll.y, Ll.z, __int_as_float(pair));
+            n_parked += __popc(m);
+        }
+        __syncwarp();
+    }
+    flush_counters(rays, traced, counters);
+    if (LOBE == LOBE_LAMBERT && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&counters->shade_lines, (unsigned long long)total);
+}
+#endif
+// one pair per thread from start to end (lights the cull does not apply to: nothing would be settled early)
+template <int LOBE, int TRAITS>
+__global__ void __launch_bounds__(128, KYD_NEE_SERIAL_MIN_BLOCKS) k_nee_serial(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters)
 {
     stage_rects();
     const int n = (int)counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)];
