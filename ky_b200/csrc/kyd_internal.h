@@ -90,7 +90,7 @@ struct WavefrontPlan
     bool split;           // KYD_FLAG_SPLIT_LIGHT_SAMPLE: vertex records for the stand-alone light-sample kernel
     bool pair_kernel;     // hot with several lights: the light loop runs in k_nee over (vertex, light) pairs (vertex records + 16-byte results)
     bool recursion;       // one of the three recursive integrators: forward pass with a per-level record, then k_unwind
-    bool fused;           // inline_queries and not KYD_FUSE_INTERSECT=0: shade also traces the path's next ray (closest hit, lobe
+    bool fused;           // headline configurations unless KYD_FUSE_INTERSECT=0: shade also traces the path's next ray (closest hit, lobe
                           // classification), so only the camera rays go through the intersect kernel
 };
 inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scene)
@@ -105,7 +105,11 @@ inline WavefrontPlan wavefront_plan(const RenderParams& rp, const DevScene& scen
     p.nee = rp.direct_sample != KYD_DS_IDLE && scene.n_lights > 0 && !p.inline_queries && !p.recursion;   // (recursion: light queries inside shade)
     p.pair_kernel = p.hot && p.nee;
     static const bool fuse_enabled = !(getenv("KYD_FUSE_INTERSECT") && getenv("KYD_FUSE_INTERSECT")[0] == '0');
-    p.fused = p.inline_queries && fuse_enabled;
+    static const bool fuse_many_enabled = !(getenv("KYD_FUSE_INTERSECT_MANY") && getenv("KYD_FUSE_INTERSECT_MANY")[0] == '0');
+    // Several lights (k_nee): a vertex' light values are pending when its continuation is traced, but a ray that leaves the scene
+    // adds the environment's light only after a SPECULAR vertex (ky.cpp:4548-4563), and those sample no lights -- nothing is
+    // pending then; a Lambert / Phong vertex' path that leaves the scene just ends, and k_accumulate adds its pending values.
+    p.fused = (p.inline_queries && fuse_enabled) || (p.pair_kernel && fuse_enabled && fuse_many_enabled);
     return p;
 }
 

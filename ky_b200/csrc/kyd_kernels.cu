@@ -854,11 +854,13 @@ static void launch_shade(int traits, bool hot, bool one_light, bool fused, int g
     else if (traits == TRAITS_AREA_SPHERE)
     {
         if (one_light) launch_shade_one_light<TRAITS_AREA_SPHERE>(fused, grid, stream, wp, w, counters, bounce);
+        else if (fused) launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_MANY, true>(grid, stream, wp, w, counters, bounce);
         else launch_shade_lobes<TRAITS_AREA_SPHERE, true, NL_MANY, false>(grid, stream, wp, w, counters, bounce);
     }
     else
     {
         if (one_light) launch_shade_one_light<TRAITS_ANY>(fused, grid, stream, wp, w, counters, bounce);
+        else if (fused) launch_shade_lobes<TRAITS_ANY, true, NL_MANY, true>(grid, stream, wp, w, counters, bounce);
         else launch_shade_lobes<TRAITS_ANY, true, NL_MANY, false>(grid, stream, wp, w, counters, bounce);
     }
 #endif
@@ -954,7 +956,11 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                     ++*launches;
                 }
                 if (plan.fused)   // the lobe queues the shade kernels of this bounce fill were consumed one bounce ago
+                {
                     cudaMemsetAsync(&counters->queue[Q_LOBE0 + 4 * ((bounce & 1) ^ 1)], 0, 4 * sizeof(unsigned long long), stream);
+                    if (plan.pair_kernel && bounce > 0)   // (and k_nee's vertex queues by the previous bounce's k_nee)
+                        cudaMemsetAsync(&counters->queue[Q_NEE0], 0, 2 * sizeof(unsigned long long), stream);
+                }
                 T(StageTimer::SHADE);
 #if !KYD_BIG_SCENE
                 if (plan.recursion)

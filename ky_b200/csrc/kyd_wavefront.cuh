@@ -870,7 +870,7 @@ KYD_DEV void shade_vertex_hot_one(const WaveParams& wp, int bounce, VertexOut* o
     out->Lo = Lo;
 }
 
-// FUSE (headline configuration with one light; wavefront_plan().fused): shade also traces the path's next ray -- closest hit,
+// FUSE (headline configurations; wavefront_plan().fused): shade also traces the path's next ray -- closest hit,
 // lobe classification, the miss -- and pushes the path straight into the NEXT bounce's lobe queue, so only camera rays go
 // through k_intersect.  That kernel had become a pure gather / scatter of path records once the two-phase traversal made its
 // arithmetic cheap (long-scoreboard bound, 2 TB/s of 32-byte sectors; profiles/r02_*): fused, its 64 B per ray never move.
@@ -1007,6 +1007,12 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
         {
             lobe_push.commit(lobe_queues);
             lobe_push.reserve(next_lobe >= 0 ? (1u << next_lobe) : 0u, slot, lobe_tails);
+            if (NL == NL_MANY)
+            {
+                // several lights: the vertex still goes to k_nee's queue (the host zeroes that tail before every bounce's shade)
+                push.commit(out_queues);
+                push.reserve(split_vertex ? 2u : 0u, slot, tails);
+            }
         }
         else
         {
@@ -1029,7 +1035,7 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     }
     if (FUSE)
         lobe_push.commit(lobe_queues);
-    else
+    if (!FUSE || NL == NL_MANY)
         push.commit(out_queues);
     if (DEFERS)
         pairs.commit(pair_queue);
