@@ -539,6 +539,29 @@ KYD_DEV void shape_sample_position(const DevShape& s, float2 u, float3* lp, floa
     *area_pdf = 1 / s.area;
 }
 
+// sphere_t::sample_direction from a point inside the sphere (ky.cpp:1422-1444): uniform point on the sphere, area pdf converted
+// with the SHADING normal -- the same statements as the inline branch below, behind a call
+struct SphereInsideSample { float3 lp, ln; float pdf; };
+__device__ __noinline__ SphereInsideSample sphere_sample_from_inside(float3 center, float radius, float area, float3 p, float3 n_shade, float2 u)
+{
+    SphereInsideSample r;
+    float3 direction = uniform_sphere_sample(u);
+    r.lp = add(center, mul(direction, radius));
+    r.ln = normalize(direction);
+    const float area_pdf = 1 / area;
+    float3 wi = sub(r.lp, p);
+    if (msq(wi) == 0)
+        r.pdf = 0;
+    else
+    {
+        wi = normalize(wi);
+        r.pdf = area_pdf * distance_sq(r.lp, p) / abs_dot(n_shade, neg(wi));
+    }
+    if (isinf(r.pdf))
+        r.pdf = 0.f;
+    return r;
+}
+
 // shape_t::sample_direction ky.cpp:1028-1051 and sphere_t's override ky.cpp:1419-1501
 template <int TRAITS = TRAITS_ANY>
 KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade, float2 u, float3* lp, float3* ln, float* pdf)
@@ -549,6 +572,13 @@ KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade,
         float radius = s.radius;
         if (distance_sq(p, center) <= radius * radius)
         {
+            if (TRAITS == TRAITS_AREA_SPHERE)
+            {
+                // (cold in the scenes the sphere-light kernels are built for, and those kernels are instruction-fetch bound)
+                const SphereInsideSample in = sphere_sample_from_inside(s.p0, s.radius, s.area, p, n_shade, u);
+                *lp = in.lp; *ln = in.ln; *pdf = in.pdf;
+                return;
+            }
             float area_pdf;
             shape_sample_position<TRAITS>(s, u, lp, ln, &area_pdf);
             float3 wi = sub(*lp, p);
@@ -610,6 +640,23 @@ KYD_DEV void shape_sample_direction(const DevShape& s, float3 p, float3 n_shade,
     }
 }
 
+// shape_t::pdf_direction (ky.cpp:1055-1090) for a sphere seen from inside: the general branch below with the kind fixed
+__device__ __noinline__ float sphere_pdf_from_inside(const DevShape& s, float3 p, float3 n_shade, float3 wi)
+{
+    Ray r;
+    r.o = offset_ray_origin(p, n_shade, wi);
+    r.d = wi;
+    r.tmax = KYD_INF;
+    float t;
+    if (!shape_hit_distance_kind(s, KYD_SHAPE_SPHERE, r, r.tmax, &t))
+        return 0.f;
+    HitGeom g = shape_hit_geom_kind(s, KYD_SHAPE_SPHERE, r, t);
+    float pdf = distance_sq(p, g.position) / (abs_dot(g.normal, neg(wi)) * s.area);
+    if (isinf(pdf))
+        pdf = 0.f;
+    return pdf;
+}
+
 // shape_t::pdf_direction ky.cpp:1055-1090 and sphere_t's override ky.cpp:1503-1513
 template <int TRAITS = TRAITS_ANY>
 KYD_DEV float shape_pdf_direction(const DevShape& s, float3 p, float3 n_shade, float3 wi)
@@ -623,6 +670,8 @@ KYD_DEV float shape_pdf_direction(const DevShape& s, float3 p, float3 n_shade, f
             return 1 / (2 * KYD_PI * (1 - cos_theta_max));
         }
     }
+    if (TRAITS == TRAITS_AREA_SPHERE)
+        return sphere_pdf_from_inside(s, p, n_shade, wi);   // (cold, behind a call: see sphere_sample_from_inside)
     Ray r;
     r.o = offset_ray_origin(p, n_shade, wi);
     r.d = wi;

@@ -895,7 +895,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
         for (int l = 0; l < scene.n_lights; ++l)
         {
             const int ls = scene.light_surface[l];
-            unique = unique && (scene.n_lights > 1 || ls != -2);
+            unique = unique && ls != -2;
             if (ls >= 0 && scene.bvh_nodes == nullptr)
                 sphere_surfaces = sphere_surfaces && scene.surf_shape[ls].kind == KYD_SHAPE_SPHERE;
         }

@@ -1235,9 +1235,10 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
             {
                 traced++;
                 float t;
-                if (!fresh && q.light_surface < 0)
+                if (TRAITS == TRAITS_ANY && !fresh && q.light_surface < 0)
                 {
-                    // closest-hit form (a light carried by several surfaces, or the environment light)
+                    // closest-hit form (a light carried by several surfaces, or the environment light; the host selects the
+                    // sphere-light kernels only where every light's query is in its occlusion form)
                     const int s = wf_closest(q.ray, &t);
                     value = nee_bsdf_resolve(q, s, t);
                 }

@@ -7,7 +7,10 @@ summarise() { # report-prefix workload-string
   python scripts/ncu_summary.py report gpurun_out/$1.ncu-rep > gpurun_out/$1_kernels.txt 2>&1
   python scripts/ncu_summary.py json gpurun_out/$1.ncu-rep gpurun_out/$1_ncu_summary.json "$2" > /dev/null 2>&1
   python scripts/ncu_summary.py stalls gpurun_out/$1.ncu-rep > gpurun_out/$1_stalls.txt 2>&1
-  for k in k_shade k_intersect k_nee k_shadow; do python scripts/line_mix.py gpurun_out/$1.ncu-rep $k 0 25 >> gpurun_out/$1_lines.txt 2>&1; done
+  for k in k_shade k_intersect k_nee k_shadow; do python scripts/line_mix.py gpurun_out/$1.ncu-rep $k 0 60 >> gpurun_out/$1_lines.txt 2>&1; done
+  for k in k_shade k_nee; do for c in stall_wait stall_short_sb stall_no_inst stall_long_sb stall_branch_resolving; do
+    echo "== $k $c" >> gpurun_out/$1_line_stalls.txt; python scripts/line_stalls.py gpurun_out/$1.ncu-rep $k 0 $c 14 >> gpurun_out/$1_line_stalls.txt 2>&1; done
+    python scripts/stall_mix.py gpurun_out/$1.ncu-rep $k 0 >> gpurun_out/$1_stall_mix.txt 2>&1; done
   rm -f gpurun_out/$1.ncu-rep
 }
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --spp-per-step 2 --e2e-steps 1 --no-cpu-baseline --no-configs > gpurun_out/${tag}_ncu.log 2>&1

@@ -10,4 +10,4 @@ print("$1 $2", round(d["value"],1), {k:round(x,1) for k,x in d["stage_ms_per_ste
 PY
 }
 run cur C5; run cur C3
-KYD_FUSE_INTERSECT_MANY=0 run nofusemany C3
+# (session P only) KYD_FUSE_INTERSECT_MANY=0 run nofusemany C3
