@@ -917,6 +917,9 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
 #ifndef KYD_SHADE_PREFETCH_MANY
 #define KYD_SHADE_PREFETCH_MANY 1
 #endif
+#ifndef KYD_PENDING_PREFETCH
+#define KYD_PENDING_PREFETCH 0   // (L2 prefetch of the previous vertex' light values one iteration ahead: shade 68.9 vs 68.0 ms on C3, no gain)
+#endif
 #ifndef KYD_SHADE_PREFETCH_SPECULAR
 #define KYD_SHADE_PREFETCH_SPECULAR 0   // (measured: 2543 vs 2544 Msamples/s on C5, no effect)
 #endif
@@ -948,6 +951,19 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
             const float4* pn = path_line(w, slot_next);
             nx0 = pn[P_ORIGIN]; nx1 = pn[P_DIRECTION]; nx2 = pn[P_BETA]; nx3 = pn[P_TAIL];
         }
+#if KYD_PENDING_PREFETCH
+        if (HOT && NL == NL_MANY && bounce > 0 && slot_next >= 0)
+        {
+            // The previous vertex' light values (k_nee's results, 16 B per light, and that vertex' beta) are read as soon as this
+            // path's record says they are pending -- a second DRAM round trip behind the record's, 60 % of this kernel's stall
+            // cycles (profiles/r02q_prof_c3_line_stalls.txt).  Their address only needs the slot, known one iteration ahead:
+            // start them towards L2 now (no registers held).
+            const char* res = reinterpret_cast<const char*>(w.nee + (size_t)slot_next * n_lights);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + n_lights * 16 - 1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(vertex_line(w, slot_next) + V_BETA));
+        }
+#endif
         bool alive = false, split_vertex = false;
         unsigned pair_mask = 0;
         int next_lobe = -1;

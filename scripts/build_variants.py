@@ -20,6 +20,8 @@ variants = {
     "nee8": ["-DKYD_NEE_MIN_BLOCKS=8"],
     "nodefer": ["-DKYD_NEE_DEFER=0"],
     "vmajor": ["-DKYD_NEE_LIGHT_MAJOR=0"],
+    "nee7": ["-DKYD_NEE_MIN_BLOCKS=7"],
+    "nee5d": ["-DKYD_NEE_MIN_BLOCKS=5"],
     "nopf": ["-DKYD_SHADE_PREFETCH=0"],
     "nopf_mb5": ["-DKYD_SHADE_PREFETCH=0", "-DKYD_SHADE_MIN_BLOCKS=5"],
     "nopf_mb6": ["-DKYD_SHADE_PREFETCH=0", "-DKYD_SHADE_MIN_BLOCKS=6"],
