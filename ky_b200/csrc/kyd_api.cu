@@ -363,7 +363,7 @@ size_t wave_bytes_per_path(const WavefrontPlan& plan, int n_lights)
 {
     size_t b = 64 + 12 * 4;                                  // path record, 2 ray queues + 2 x 4 lobe queues + 2 vertex queues
     if (plan.nee && !plan.pair_kernel) b += (size_t)n_lights * (128 + 2 * 4);   // light-sampling lines + pair queues
-    if (plan.pair_kernel) b += (size_t)n_lights * 16;          // k_nee results
+    if (plan.pair_kernel) b += (size_t)(n_lights + 1) * 16;    // k_nee results + per-vertex summary
     if (plan.split || plan.pair_kernel) b += 96;               // vertex records
     return b;   // (+ 32 bytes per level for the recursive integrators, added by the caller)
 }
@@ -394,7 +394,7 @@ int render_to_device(kyd_ctx* ctx, const kyd_render_desc* d, float* film_dev, cu
         if (capacity < 1024) capacity = 1024;
         // light-sampling lines (128 B per light and path) and vertex records (96 B per path) only where the plan uses them
         const WavefrontPlan plan = wavefront_plan(rp, ctx->scene);
-        const int nee_lights = plan.nee ? ctx->scene.n_lights : 0;
+        const int nee_lights = plan.nee ? ctx->scene.n_lights + (plan.pair_kernel ? 1 : 0) : 0;   // (+1: k_nee's per-vertex summaries)
         // Results do not depend on the wave size, so memory decides it where it is short (a GPU shared with other work,
         // many lights: 136 B per light and path): the default is capped by what is free now, and an allocation that
         // still fails is retried with half the wave down to 64 Ki paths.

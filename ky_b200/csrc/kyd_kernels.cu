@@ -938,7 +938,8 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
             wp.direct_only = direct_only ? 1 : 0;
             wp.split_light_sample = (rp.flags & KYD_FLAG_SPLIT_LIGHT_SAMPLE) ? 1 : 0;
             wp.no_pending = nee ? 0 : 1;
-            wp.pair_kernel = plan.pair_kernel ? 1 : 0;
+            // (2: the sphere-light k_nee also leaves a per-vertex summary behind its results, kyd_wavefront.cuh add_pending)
+            wp.pair_kernel = plan.pair_kernel ? ((KYD_NEE_DEFER && KYD_NEE_LIGHT_MAJOR && KYD_NEE_SUMMARY && !KYD_BIG_SCENE && traits == TRAITS_AREA_SPHERE) ? 2 : 1) : 0;
             wp.recursion = plan.recursion ? rp.integrator : 0;
 
             // queue tails start at zero; the camera rays are generated inside the first intersect launch

@@ -99,6 +99,8 @@ struct WaveParams
 KYD_DEV float4* path_line(const WaveBuffers& w, int slot) { return w.path + (size_t)slot * PATH_UNITS; }
 KYD_DEV float4* nee_line(const WaveBuffers& w, long long plane, int light, int slot) { return w.nee + ((size_t)light * plane + slot) * NEE_UNITS; }
 KYD_DEV float4* vertex_line(const WaveBuffers& w, int slot) { return w.vertex + (size_t)slot * VERTEX_UNITS; }
+// k_nee's per-vertex summaries {beta * sum over lights, complete}: behind the n_lights results of every slot (wp.pair_kernel == 2)
+KYD_DEV float4* nee_summary(const WaveBuffers& w, long long plane, int n_lights) { return w.nee + (size_t)plane * n_lights; }
 // record of one recursion level of a path (recursive integrators): {Lo.rgb, |cos|}, {f.rgb, pdf}; level-major planes
 KYD_DEV float4* level_line(const WaveBuffers& w, long long plane, int level, int slot) { return w.levels + ((size_t)level * plane + slot) * 2; }
 
@@ -257,8 +259,16 @@ KYD_DEV void store_path_tail(float4* p, float3 beta, float3 Lo, unsigned long lo
 // Lo += beta_vertex * (sum over lights of the vertex' estimator values), ky.cpp:4575-4576.  `pending` = the lights that
 // got a light-sampling line; the others' values are exactly +0 (no query of theirs could contribute) and adding +0 to
 // the running sum, which starts at +0 and therefore is never -0, changes nothing -- so they are skipped, in light order.
-KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsigned pending, float3 Lo, bool pair_kernel = false)
+KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsigned pending, float3 Lo, int pair_kernel = 0)
 {
+    if (pending != 0 && pair_kernel == 2)
+    {
+        // k_nee (light-major form) leaves beta_vertex * (the sum below) behind for every vertex whose pairs it finished in light
+        // order: one 32-byte sector instead of the lights' values and the vertex record's beta
+        const float4 sum = nee_summary(w, plane, c_scene.n_lights)[slot];
+        if (sum.w != 0.f)
+            return add(Lo, V3(sum.x, sum.y, sum.z));
+    }
     if (pending != 0 && pair_kernel)
     {
         // k_nee's results: every light of the vertex, in light order -- sample_all_light's own sum (ky.cpp:3864-3869)
@@ -420,7 +430,7 @@ __global__ void __launch_bounds__(256, KYD_INTERSECT_MIN_BLOCKS) k_intersect(Wav
                 // Lo += beta * environment_lighting after a specular bounce
                 PathState st;
                 unpack_path(st, o, d, p[P_BETA], p[P_TAIL]);
-                float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel != 0);
+                float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel);
                 Lo = add(Lo, cmulc(st.beta, environment_lighting()));
                 store_path_ray(p, r.o, o.w, r.d, flags & FLAG_PREV_SPECULAR); // pending consumed
                 store_path_tail(p, st.beta, Lo, st.rng);
@@ -571,7 +581,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
     const int surface = st.surface();
 
     // light gathered at the previous vertex (see file header)
-    float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel != 0);
+    float3 Lo = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel);
     unsigned new_pending = 0;   // lights that get a light-sampling line at this vertex
 
     HitGeom g = shape_hit_geom(surface_shape(surface), r, st.t);
@@ -1058,10 +1068,25 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     flush_counters(counts.ref_rays, counts.traced, counters);
 }
 
+// blocks per SM the register allocation aims at.  The mirror / glass kernels and the multi-light Lambert / Phong kernels (which
+// hand their light loop to k_nee) are short and wait for their records (long-scoreboard 2.6-6 stalls per issue at 16 warps
+// per SM, profiles/r02_c5_stalls.txt, r02_c3_stalls.txt): they can trade registers for warps in flight.
+#ifndef KYD_SHADE_MIN_BLOCKS_SPECULAR
+#define KYD_SHADE_MIN_BLOCKS_SPECULAR KYD_SHADE_MIN_BLOCKS
+#endif
+#ifndef KYD_SHADE_MIN_BLOCKS_MANY
+#define KYD_SHADE_MIN_BLOCKS_MANY KYD_SHADE_MIN_BLOCKS
+#endif
+constexpr int shade_min_blocks(int lobe, bool hot, int nl)
+{
+    return (hot && (lobe == LOBE_MIRROR || lobe == LOBE_FRESNEL)) ? KYD_SHADE_MIN_BLOCKS_SPECULAR
+         : (hot && nl == NL_MANY) ? KYD_SHADE_MIN_BLOCKS_MANY : KYD_SHADE_MIN_BLOCKS;
+}
+
 // one kernel per lobe: each gets the register allocation its own code needs (the Lambert kernel, which
 // shades most vertices, does not pay for Phong's pow() or the dielectric's Fresnel terms)
 template <int LOBE, int TRAITS, bool HOT, int NL, bool FUSE>
-__global__ void __launch_bounds__(SHADE_THREADS, KYD_SHADE_MIN_BLOCKS) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
+__global__ void __launch_bounds__(SHADE_THREADS, shade_min_blocks(LOBE, HOT, NL)) k_shade(WaveParams wp, WaveBuffers w, DevCounters* __restrict__ counters, int bounce)
 {
     shade_queue<LOBE, TRAITS, HOT, NL, FUSE>(wp, w, counters, bounce);
 }
@@ -1135,6 +1160,9 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 #ifndef KYD_NEE_LIGHT_MAJOR
 #define KYD_NEE_LIGHT_MAJOR 1
 #endif
+#ifndef KYD_NEE_SUMMARY
+#define KYD_NEE_SUMMARY 1   // per-vertex sums behind the results (wp.pair_kernel == 2): the next stage reads one 32-byte sector per vertex instead of 144 bytes
+#endif
 #if KYD_NEE_DEFER
 // Deferred BSDF-sampled queries.  bsdf_query_certainly_misses settles all but a few per cent of a sphere light's
 // BSDF-sampled queries, but a warp holds 32 pairs: with a survivor in most warps, nearly every warp walked the exact set-up
@@ -1150,6 +1178,9 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
 {
     stage_rects();
     __shared__ float4 s_parked[4][64];                   // {Ll.rgb, pair index}: < 32 left over + up to 32 new per iteration
+#if KYD_NEE_LIGHT_MAJOR && KYD_NEE_SUMMARY
+    __shared__ float4 s_run[128];                        // the running sum over the lights of this lane's vertex; w: a pair of it was parked
+#endif
     const int n = (int)counters->queue[Q_NEE0 + (LOBE == LOBE_PHONG)];
     const int* __restrict__ queue = w.queue_nee[LOBE == LOBE_PHONG];
     const int n_lights = c_scene.n_lights;
@@ -1267,11 +1298,35 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
             const float3 Lb = fresh ? KYD_BLACK : value;
             if (fresh)
                 Ll = value;
+            const float3 e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
             if (!park)
-            {
-                const float3 e = add(mul(Lb, 0.5f), mul(Ll, 0.5f));
                 w.nee[(size_t)slot * n_lights + l] = make_float4(e.x, e.y, e.z, 0.f);
+#if KYD_NEE_LIGHT_MAJOR && KYD_NEE_SUMMARY
+            if (fresh)
+            {
+                // sample_all_light's sum (ky.cpp:3864-3869) as the lane walks its vertex' lights in order, then L += beta * Ld
+                // (ky.cpp:4575-4576) left as 16 bytes for the consumers (add_pending).  A parked pair's value arrives out of order:
+                // its vertex is marked and summed by the reader from the lights' values instead.
+                float4 run = l == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : s_run[threadIdx.x];
+                if (park)
+                    run.w = 1.f;
+                else
+                {
+                    const float3 Ld = add(V3(run.x, run.y, run.z), e);
+                    run.x = Ld.x; run.y = Ld.y; run.z = Ld.z;
+                }
+                if (l == n_lights - 1)
+                {
+                    // (the vertex' beta is read again here, an L2 hit, rather than kept in three registers across the walk: the
+                    // kernel sits exactly at the 80 registers that six blocks per SM allow)
+                    const float4 vb_again = __ldcg(&v[V_BETA]);
+                    const float3 P = cmulc(V3(vb_again.x, vb_again.y, vb_again.z), V3(run.x, run.y, run.z));
+                    nee_summary(w, wp.plane, n_lights)[slot] = make_float4(P.x, P.y, P.z, run.w == 0.f ? 1.f : 0.f);
+                }
+                else
+                    s_run[threadIdx.x] = run;
             }
+#endif
         }
         if (fresh)
         {
@@ -1685,7 +1740,7 @@ __global__ void __launch_bounds__(256) k_accumulate(WaveParams wp, WaveBuffers w
             {
                 PathState st;
                 unpack_path(st, p[P_ORIGIN], p[P_DIRECTION], p[P_BETA], p[P_TAIL]);
-                Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel != 0);
+                Li = add_pending(w, wp.plane, slot, st.pending(), st.Lo, wp.pair_kernel);
             }
             L = add(L, mul(Li, wp.rp.weight));
         }

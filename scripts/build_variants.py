@@ -21,6 +21,12 @@ variants = {
     "nodefer": ["-DKYD_NEE_DEFER=0"],
     "vmajor": ["-DKYD_NEE_LIGHT_MAJOR=0"],
     "nee7": ["-DKYD_NEE_MIN_BLOCKS=7"],
+    "nosum": ["-DKYD_NEE_SUMMARY=0"],
+    "sumlive": ["-DKYD_NEE_SUMMARY=2"],
+    "sum5": ["-DKYD_NEE_MIN_BLOCKS=5"],
+    "occ6": ["-DKYD_SHADE_MIN_BLOCKS_SPECULAR=6", "-DKYD_SHADE_MIN_BLOCKS_MANY=6"],
+    "occ8": ["-DKYD_SHADE_MIN_BLOCKS_SPECULAR=8", "-DKYD_SHADE_MIN_BLOCKS_MANY=8"],
+    "occ5": ["-DKYD_SHADE_MIN_BLOCKS_SPECULAR=5", "-DKYD_SHADE_MIN_BLOCKS_MANY=5"],
     "nee5d": ["-DKYD_NEE_MIN_BLOCKS=5"],
     "nopf": ["-DKYD_SHADE_PREFETCH=0"],
     "nopf_mb5": ["-DKYD_SHADE_PREFETCH=0", "-DKYD_SHADE_MIN_BLOCKS=5"],
