@@ -929,6 +929,59 @@ KYD_DEV int surface_material(int i) { return c_scene.surf_material[i]; }
 KYD_DEV int surface_light(int i) { return c_scene.surf_light[i]; }
 #endif
 
+// Per-surface data of the vertex being shaded, in shared memory (the one-light headline kernels; KYD_SURFACE_SMEM=1).  A vertex reads its surface's
+// normal / centre, material parameters and light index by the surface index of ITS path: in constant memory that is a load
+// with up to a dozen different addresses in a warp, replayed once per address (what made k_nee's per-light loads cost 12 % of
+// that kernel, profiles/r02_ab_variants.txt); shared memory serves different addresses in one pass.  The material is copied
+// per surface, which also removes the surface -> material indirection.
+struct SurfaceTable
+{
+    DevShape shape[KYD_MAX_SURFACES];
+    DevMaterial material[KYD_MAX_SURFACES];   // materials[surf_material[i]]
+    int light[KYD_MAX_SURFACES];
+};
+// (measured: C5 2638 vs 2644-2666 Msamples/s without it -- a dozen loads per vertex, not on the critical path: left off)
+#ifndef KYD_SURFACE_SMEM
+#define KYD_SURFACE_SMEM 0
+#endif
+#if !KYD_BIG_SCENE && KYD_SURFACE_SMEM
+#define KYD_HAS_SURFACE_TABLE 1
+KYD_DEV SurfaceTable& surface_table()
+{
+    __shared__ SurfaceTable t;
+    return t;
+}
+// every thread of the block, once, before the first vertex
+KYD_DEV void stage_surfaces()
+{
+    SurfaceTable& t = surface_table();
+    const int n = c_scene.n_surfaces;
+    constexpr int WS = (int)(sizeof(DevShape) / 4), WM = (int)(sizeof(DevMaterial) / 4);
+    unsigned* shape_words = reinterpret_cast<unsigned*>(t.shape);
+    const unsigned* shape_src = reinterpret_cast<const unsigned*>(c_scene.surf_shape);
+    for (int i = threadIdx.x; i < n * WS; i += blockDim.x)
+        shape_words[i] = shape_src[i];
+    unsigned* material_words = reinterpret_cast<unsigned*>(t.material);
+    for (int i = threadIdx.x; i < n * WM; i += blockDim.x)
+    {
+        const int k = i / WM, f = i - k * WM;
+        material_words[i] = reinterpret_cast<const unsigned*>(&c_scene.materials[c_scene.surf_material[k]])[f];
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        t.light[i] = c_scene.surf_light[i];
+    __syncthreads();
+}
+template <bool TABLE> KYD_DEV const DevShape& surface_shape_of(int i) { return TABLE ? surface_table().shape[i] : surface_shape(i); }
+template <bool TABLE> KYD_DEV const DevMaterial& surface_material_of(int i) { return TABLE ? surface_table().material[i] : c_scene.materials[surface_material(i)]; }
+template <bool TABLE> KYD_DEV int surface_light_of(int i) { return TABLE ? surface_table().light[i] : surface_light(i); }
+#else
+#define KYD_HAS_SURFACE_TABLE 0
+KYD_DEV void stage_surfaces() {}
+template <bool TABLE> KYD_DEV const DevShape& surface_shape_of(int i) { return surface_shape(i); }
+template <bool TABLE> KYD_DEV const DevMaterial& surface_material_of(int i) { return c_scene.materials[surface_material(i)]; }
+template <bool TABLE> KYD_DEV int surface_light_of(int i) { return surface_light(i); }
+#endif
+
 // ---- scene traversal ky.cpp:3077-3088, 3172-3206 ------------------------------------------------------------
 
 // The distance at which shape_t::intersect would report a hit if tmax were unbounded: the same arithmetic and the
@@ -1601,9 +1654,10 @@ KYD_DEV float3 areal_radiance(const DevLight& l, float3 light_normal, float3 wo)
     return (dot(light_normal, wo) > 0) ? l.color : KYD_BLACK;
 }
 
+template <bool TABLE = false>
 KYD_DEV float3 surface_emission(int surface, const HitGeom& g) // ky.cpp:3084
 {
-    int li = surface_light(surface);
+    int li = surface_light_of<TABLE>(surface);
     return li >= 0 ? areal_radiance(c_scene.lights[li], g.normal, g.wo) : KYD_BLACK;
 }
 

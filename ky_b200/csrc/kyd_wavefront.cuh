@@ -52,7 +52,9 @@ enum { Q_RAY0 = 0, Q_RAY1 = 1, Q_NEE0 = 2 /* +lobe (Lambert, Phong): vertices, s
 #ifndef KYD_SHADE_MIN_BLOCKS
 #define KYD_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef SHADE_THREADS
 #define SHADE_THREADS 128
+#endif
 
 // number of lights as a compile-time property of the headline shade kernels: one light = its queries are traced inside
 // shade, several = one light-sampling line per (vertex, light) for the shadow stage; NL_ANY decides at run time
@@ -299,9 +301,10 @@ KYD_DEV float3 add_pending(const WaveBuffers& w, long long plane, int slot, unsi
 }
 
 // the lobe material_t::scattering will build for this hit (ky.cpp:2587-2671); pure function of the hit
+template <bool TABLE = false>
 KYD_DEV int classify_lobe(int surface, const Ray& r, float t)
 {
-    const DevMaterial& m = c_scene.materials[surface_material(surface)];
+    const DevMaterial& m = surface_material_of<TABLE>(surface);
     if (m.kind == KYD_MAT_MATTE) return LOBE_LAMBERT;
     if (m.kind == KYD_MAT_MIRROR) return LOBE_MIRROR;
     if (m.kind == KYD_MAT_GLASS) return LOBE_FRESNEL;
@@ -745,7 +748,7 @@ KYD_DEV void shade_vertex(const WaveParams& wp, const WaveBuffers& w, int slot, 
 // The draws are the reference's: random_bsdf, random_light (ky.cpp:3866-3868, g++ order), then the continuation's pair.
 template <int LOBE, int TRAITS, bool FUSE>
 KYD_DEV void shade_vertex_hot_one(const WaveParams& wp, int bounce, VertexOut* out, ShadeCounts* counts,
-                                  float4 rec0, float4 rec1, float4 rec2, float4 rec3)
+                                  float4 rec0, float4 rec1, float4 rec2, float4 rec3, bool whole_block = false)
 {
     constexpr bool OCC = TRAITS != TRAITS_ANY;
     PathState st;
@@ -758,9 +761,10 @@ KYD_DEV void shade_vertex_hot_one(const WaveParams& wp, int bounce, VertexOut* o
     const int surface = st.surface();
     float3 Lo = st.Lo;   // (no light is ever pending in this configuration)
 
-    HitGeom g = shape_hit_geom(surface_shape(surface), r, st.t);
+    constexpr bool TABLE = KYD_HAS_SURFACE_TABLE != 0;   // (shade_queue staged it)
+    HitGeom g = shape_hit_geom(surface_shape_of<TABLE>(surface), r, st.t);
     if (bounce == 0 || (st.flags & FLAG_PREV_SPECULAR))
-        Lo = add(Lo, cmulc(beta, surface_emission(surface, g)));
+        Lo = add(Lo, cmulc(beta, surface_emission<TABLE>(surface, g)));
 
     out->alive = false;
     out->o = st.o;
@@ -775,7 +779,7 @@ KYD_DEV void shade_vertex_hot_one(const WaveParams& wp, int bounce, VertexOut* o
     out->hit_t = KYD_INF;
     if (bounce < wp.rp.max_depth)
     {
-        const DevMaterial& m = c_scene.materials[surface_material(surface)];
+        const DevMaterial& m = surface_material_of<TABLE>(surface);
         Bsdf b;
         b.f = frame_from_z(g.normal);
         b.t = KYD_BLACK;
@@ -796,6 +800,10 @@ KYD_DEV void shade_vertex_hot_one(const WaveParams& wp, int bounce, VertexOut* o
 #pragma unroll 1
         for (int trip = 0; trip < 3; ++trip)
         {
+#if KYD_SHADE_LOCKSTEP & 4
+            if (whole_block && trip > 0)
+                __syncthreads();   // (every thread of the block shades a vertex in this iteration: see shade_queue)
+#endif
             // the ray of this trip, the starting state of its walk, and what its answer is worth
             NeeRay q;
             q.active = false;
@@ -888,6 +896,8 @@ template <int LOBE, int TRAITS, bool HOT, int NL, bool FUSE>
 KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters* __restrict__ counters, int bounce)
 {
     constexpr bool HOT_ONE = HOT && NL == NL_ONE && (LOBE == LOBE_LAMBERT || LOBE == LOBE_PHONG);
+    if (HOT_ONE)
+        stage_surfaces();
     if (HOT_ONE || FUSE)
         stage_rects();   // this kernel traces scene queries itself
     const int parity = bounce & 1;
@@ -927,6 +937,9 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
 #ifndef KYD_SHADE_PREFETCH_MANY
 #define KYD_SHADE_PREFETCH_MANY 1
 #endif
+#ifndef KYD_SHADE_LOCKSTEP
+#define KYD_SHADE_LOCKSTEP 3   // (C5: 0 -> 2655, 2 -> 2685, 3 -> 2736-2755, 7 = also between the trips -> 2705 Msamples/s)
+#endif
 #ifndef KYD_PENDING_PREFETCH
 #define KYD_PENDING_PREFETCH 0   // (L2 prefetch of the previous vertex' light values one iteration ahead: shade 68.9 vs 68.0 ms on C3, no gain)
 #endif
@@ -953,6 +966,12 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
     }
     for (int i0 = blockIdx.x * blockDim.x; i0 < n; i0 += stride, ia += stride) // block-uniform trip count
     {
+#if KYD_SHADE_LOCKSTEP
+        // (experiment: the block's four warps enter every vertex together, so that they fetch the same instruction lines at
+        // about the same time -- the one-light kernels are instruction-fetch bound; bit 0: Lambert, bit 1: Phong)
+        if (HOT_ONE && (((KYD_SHADE_LOCKSTEP & 1) && LOBE == LOBE_LAMBERT) || ((KYD_SHADE_LOCKSTEP & 2) && LOBE == LOBE_PHONG)))
+            __syncthreads();
+#endif
         const long long i2 = ia + (PREFETCH ? 2ll : 1ll) * stride;
         const int slot_ahead = i2 < n ? queue[i2] : -1;
         float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0, nx2 = nx0, nx3 = nx0;
@@ -987,7 +1006,7 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
             }
             VertexOut v;
             if (HOT_ONE)
-                shade_vertex_hot_one<LOBE, TRAITS, FUSE>(wp, bounce, &v, &counts, rec0, rec1, rec2, rec3);
+                shade_vertex_hot_one<LOBE, TRAITS, FUSE>(wp, bounce, &v, &counts, rec0, rec1, rec2, rec3, i0 + (int)blockDim.x <= n);
             else
                 shade_vertex<LOBE, TRAITS, HOT, NL>(wp, w, slot, bounce, n_lights, &v, &counts, rec0, rec1, rec2, rec3);
             pair_mask = v.pairs;
@@ -1010,7 +1029,7 @@ KYD_DEV void shade_queue(const WaveParams& wp, const WaveBuffers& w, DevCounters
                 {
                     Ray nr;
                     nr.o = v.o; nr.d = v.d; nr.tmax = KYD_INF;
-                    next_lobe = classify_lobe(v.hit_surface, nr, v.hit_t);
+                    next_lobe = classify_lobe<HOT_ONE && KYD_HAS_SURFACE_TABLE != 0>(v.hit_surface, nr, v.hit_t);
                     v.flags |= (v.hit_surface + 1) << FLAG_SURFACE_SHIFT;
                     hit_t = v.hit_t;
                 }
@@ -1160,6 +1179,9 @@ __global__ void __launch_bounds__(128) k_light_sample(WaveParams wp, WaveBuffers
 #ifndef KYD_NEE_LIGHT_MAJOR
 #define KYD_NEE_LIGHT_MAJOR 1
 #endif
+#ifndef KYD_NEE_LOCKSTEP
+#define KYD_NEE_LOCKSTEP 0
+#endif
 #ifndef KYD_NEE_SUMMARY
 #define KYD_NEE_SUMMARY 1   // per-vertex sums behind the results (wp.pair_kernel == 2): the next stage reads one 32-byte sector per vertex instead of 144 bytes
 #endif
@@ -1198,11 +1220,25 @@ __global__ void __launch_bounds__(128, KYD_NEE_MIN_BLOCKS) k_nee(WaveParams wp, 
     int group = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int l_fresh = 0;
     unsigned rays = 0, traced = 0;
+#if KYD_NEE_LOCKSTEP
+    // The block's warps enter their new-pairs iterations together (as many of them as EVERY warp of the block has: the block's
+    // last warp has the fewest groups), so that they fetch the same instruction lines at about the same time: the kernel is
+    // instruction-fetch sensitive (profiles/r02_ab_variants.txt).  Parked-batch iterations run between barriers, unsynchronised.
+    const int last_warp = ((blockIdx.x + 1) * blockDim.x - 1) >> 5;
+    int lockstep_left = KYD_NEE_LIGHT_MAJOR && last_warp < n_groups ? ((n_groups - last_warp + warps_total - 1) / warps_total) * n_lights : 0;
+#endif
     for (;;)
     {
         const bool fresh = n_parked < 32 && group < n_groups; // warp-uniform: new pairs while there are any and no full batch waits
         if (!fresh && n_parked == 0)
             break;
+#if KYD_NEE_LOCKSTEP
+        if (fresh && lockstep_left > 0)
+        {
+            --lockstep_left;
+            __syncthreads();
+        }
+#endif
         int pair = -1;                                   // vertex | light << 24
         float3 Ll = KYD_BLACK;
         if (fresh)

@@ -22,6 +22,13 @@ variants = {
     "vmajor": ["-DKYD_NEE_LIGHT_MAJOR=0"],
     "nee7": ["-DKYD_NEE_MIN_BLOCKS=7"],
     "nosum": ["-DKYD_NEE_SUMMARY=0"],
+    "lock1": ["-DKYD_SHADE_LOCKSTEP=1"],
+    "t256": ["-DSHADE_THREADS=256", "-DKYD_SHADE_MIN_BLOCKS=2"],
+    "t192": ["-DSHADE_THREADS=192", "-DKYD_SHADE_MIN_BLOCKS=2"],
+    "lock7": ["-DKYD_SHADE_LOCKSTEP=7"],
+    "neelock": ["-DKYD_SHADE_LOCKSTEP=3", "-DKYD_NEE_LOCKSTEP=1"],
+    "lock2": ["-DKYD_SHADE_LOCKSTEP=2"],
+    "lock3": ["-DKYD_SHADE_LOCKSTEP=3"],
     "sumlive": ["-DKYD_NEE_SUMMARY=2"],
     "sum5": ["-DKYD_NEE_MIN_BLOCKS=5"],
     "occ6": ["-DKYD_SHADE_MIN_BLOCKS_SPECULAR=6", "-DKYD_SHADE_MIN_BLOCKS_MANY=6"],
