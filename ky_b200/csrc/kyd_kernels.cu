@@ -909,7 +909,14 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
     // (blocks per SM; measured flat between 8 and 24, profiles/r01_ab_variants.txt; KYD_GRID256 / KYD_GRID128 override them for experiments)
     static const int grid256_per_sm = getenv("KYD_GRID256") ? atoi(getenv("KYD_GRID256")) : 16;
     static const int grid128_per_sm = getenv("KYD_GRID128") ? atoi(getenv("KYD_GRID128")) : 24;
+    // The shade kernels (launch bounds: four 128-thread blocks per SM) run fastest as ONE resident wave of persistent blocks --
+    // every further block pays the shared-memory staging and the queue-count loads again, and the lockstep barrier works on
+    // blocks that start together (C5 shade 80.9 ms at 4 blocks per SM, 84.2 at 24, 87.1 at 48; C3 shade 53.8 / 58.9 / 63.9);
+    // k_nee (six resident blocks per SM) wants several waves (profiles/r02_ab_variants.txt).  KYD_GRID_SHADE overrides.
+    static const int grid_shade_per_sm = getenv("KYD_GRID_SHADE") ? atoi(getenv("KYD_GRID_SHADE")) : KYD_SHADE_MIN_BLOCKS;
+    static const int grid_nee_per_sm = getenv("KYD_GRID_NEE") ? atoi(getenv("KYD_GRID_NEE")) : 36;
     const int grid256 = sm_count * grid256_per_sm, grid128 = sm_count * grid128_per_sm;
+    const int grid_shade = sm_count * grid_shade_per_sm, grid_nee = sm_count * grid_nee_per_sm;
 
     if (!(rp.flags & KYD_FLAG_ACCUMULATE))
     {
@@ -972,7 +979,7 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                 }
                 else
 #endif
-                    launch_shade(traits, hot, plan.inline_queries, plan.fused, grid128, stream, wp, w, counters, bounce);
+                    launch_shade(traits, hot, plan.inline_queries, plan.fused, grid_shade, stream, wp, w, counters, bounce);
                 T(-1);
                 *launches += 4;
                 if (plan.pair_kernel)
@@ -983,18 +990,18 @@ void launch_render_wavefront(const RenderParams& rp, const DevScene& scene, Wave
                     if (traits == TRAITS_AREA_SPHERE)
                     {
 #if KYD_NEE_DEFER
-                        k_nee<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
-                        k_nee<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid_nee, 128, 0, stream>>>(wp, w, counters);
+                        k_nee<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid_nee, 128, 0, stream>>>(wp, w, counters);
 #else
-                        k_nee_serial<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
-                        k_nee_serial<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_LAMBERT, TRAITS_AREA_SPHERE><<<grid_nee, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_PHONG, TRAITS_AREA_SPHERE><<<grid_nee, 128, 0, stream>>>(wp, w, counters);
 #endif
                     }
                     else
 #endif
                     {
-                        k_nee_serial<LOBE_LAMBERT, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
-                        k_nee_serial<LOBE_PHONG, TRAITS_ANY><<<grid128, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_LAMBERT, TRAITS_ANY><<<grid_nee, 128, 0, stream>>>(wp, w, counters);
+                        k_nee_serial<LOBE_PHONG, TRAITS_ANY><<<grid_nee, 128, 0, stream>>>(wp, w, counters);
                     }
                     T(-1);
                     *launches += 2;
