@@ -23,6 +23,7 @@ variants = {
     "nee7": ["-DKYD_NEE_MIN_BLOCKS=7"],
     "nosum": ["-DKYD_NEE_SUMMARY=0"],
     "lock1": ["-DKYD_SHADE_LOCKSTEP=1"],
+    "smb5": ["-DKYD_SHADE_MIN_BLOCKS=5"],
     "t256": ["-DSHADE_THREADS=256", "-DKYD_SHADE_MIN_BLOCKS=2"],
     "t192": ["-DSHADE_THREADS=192", "-DKYD_SHADE_MIN_BLOCKS=2"],
     "lock7": ["-DKYD_SHADE_LOCKSTEP=7"],
