@@ -179,3 +179,39 @@ def test_errors_are_reported_not_swallowed(device):
     with pytest.raises(RuntimeError, match="before kyd_upload_scene"):
         fresh.render(ky.render_desc(8, 8, 1))
     fresh.close()
+
+
+_SWITCH_CHILD = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.environ["KY_TESTS"]); sys.path.insert(0, os.path.dirname(os.environ["KY_TESTS"]))
+import cases, ky_b200 as ky
+films = np.load(os.path.join(os.environ["KY_TESTS"], "golden", "golden_films.npz"))
+dev = ky.Device(0)
+bad = []
+for name, sk, integ, ds, depth, spp in cases.film_cases():
+    if integ != ky.INT_PT_ITERATION or ds != ky.DS_BOTH_MIS:
+        continue
+    for wave in (0, 1000):
+        dev.set_wave_paths(wave)
+        dev.upload(cases.make_scene(sk))
+        got = dev.render(ky.render_desc(cases.W, cases.H, spp, integrator=integ, max_depth=depth, direct_sample=ds, flags=ky.FLAG_CLAMP))
+        if (np.ascontiguousarray(got).view(np.uint32) != films[name].view(np.uint32)).any() or dev.stats().rays != int(films[name + "#rays"][0]):
+            bad.append((name, wave))
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+"""
+
+
+@pytest.mark.parametrize("env", [{"KYD_FUSE_INTERSECT": "0"}, {"KYD_FUSE_INTERSECT_MANY": "0"},
+                                 {"KYD_GRID_SHADE": "7", "KYD_GRID_NEE": "5", "KYD_GRID256": "3"},
+                                 {"KYD_GRID_SHADE": "1", "KYD_GRID_NEE": "1", "KYD_GRID256": "1"}],
+                         ids=["unfused", "unfused_many", "odd_grids", "one_block_per_sm"])
+def test_run_time_switches_do_not_change_films(env):
+    """The library's run-time knobs (intersect stage fused into shade or not -- for one light and for several --, grid sizes of
+    the persistent kernels) are read once per process: a child process renders every headline-configuration film with them
+    set, at two wave sizes, and compares with the reference-generated golden films bit for bit."""
+    import subprocess, sys
+    e = dict(os.environ, KY_TESTS=HERE, **env)
+    r = subprocess.run([sys.executable, "-c", _SWITCH_CHILD], env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
